@@ -1,0 +1,159 @@
+"""Validates the C oracle against an independent float64 autograd derivation (tests/refmodel.py).
+
+The reference has no tests or golden vectors for this path (PARITY UNPINNED), so the oracle is
+double-derived: hand-written Caffe-order backward (C) vs torch.autograd (float64)."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+import refmodel as R
+
+
+def relerr(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30))
+
+
+def make_state(cfg, seed, mode):
+    rng = np.random.default_rng(seed)
+    a = O.init_params(cfg, False, rng, mode)
+    c = O.init_params(cfg, True, rng, mode)
+    at = (a + rng.normal(0, 1e-3, a.size)).astype(np.float32) if mode != "caffe" else a.copy()
+    ct = (c + rng.normal(0, 1e-3, c.size)).astype(np.float32) if mode != "caffe" else c.copy()
+    return O.OracleState(cfg, a, c, at, ct)
+
+
+def to64(st):
+    d = {k: np.asarray(getattr(st, k), np.float64) for k in
+         ("actor", "critic", "actor_target", "critic_target", "actor_m", "actor_v", "critic_m", "critic_v")}
+    d["actor_iter"], d["critic_iter"] = st.actor_iter, st.critic_iter
+    return d
+
+
+@pytest.mark.parametrize("S,B,hidden,mode", [
+    (59, 32, (1024, 512, 256, 128), "caffe"),   # BASELINE cfg1: reference-native
+    (59, 32, (1024, 512, 256, 128), "warm"),
+    (58, 64, (96, 64, 48, 32), "warm"),
+    (77, 16, (128, 64, 32, 16), "warm"),
+])
+def test_single_update_matches_autograd(S, B, hidden, mode):
+    cfg = O.make_config(state_size=S, batch=B, hidden=hidden)
+    st = make_state(cfg, 7, mode)
+    rng = np.random.default_rng(11)
+    batch = O.synth_batch(cfg, rng, p_term=0.25)
+    ref, dia = R.update(cfg, to64(st), *batch)
+    loss, avgq = st.update(*batch, taps=True)
+    t = st.last_taps
+    assert relerr(t["y"], dia["y"]) < 1e-6
+    assert relerr(t["q"], dia["q"]) < 2e-5
+    assert abs(loss - dia["critic_loss"]) <= 2e-5 * abs(dia["critic_loss"]) + 1e-9
+    assert relerr(t["critic_grad"], dia["critic_grad"]) < 5e-5
+    assert relerr(t["a_pi"].reshape(B, 10), dia["a_pi"]) < 2e-5
+    assert relerr(t["q_pi"], dia["q_pi"]) < 1e-4
+    assert abs(avgq - dia["avg_q"]) <= 1e-4 * abs(dia["avg_q"]) + 1e-7
+    assert relerr(t["d_raw"].reshape(B, 10), dia["d_raw"]) < 1e-4
+    assert relerr(t["d_inv"].reshape(B, 10), dia["d_inv"]) < 1e-4
+    assert relerr(t["actor_grad"], dia["actor_grad"]) < 1e-4
+    assert abs(t["critic_gnorm"][0] - dia["critic_gnorm"]) <= 5e-5 * dia["critic_gnorm"]
+    assert abs(t["actor_gnorm"][0] - dia["actor_gnorm"]) <= 1e-4 * dia["actor_gnorm"]
+    # post-update state: Adam's first step is ~lr*sign(g) so weights agree to float rounding
+    # wherever |g| >> eps; compare with an absolute tolerance scaled by the step size.
+    assert np.abs(st.critic - ref["critic"]).max() < 0.02 * cfg.critic_lr + 1e-7
+    assert np.abs(st.actor - ref["actor"]).max() < 0.02 * cfg.actor_lr + 1e-7
+    assert relerr(st.critic_m, ref["critic_m"]) < 1e-4
+    assert relerr(st.actor_m, ref["actor_m"]) < 1e-4
+    assert relerr(st.critic_v, ref["critic_v"]) < 2e-4
+    assert np.abs(st.critic_target - ref["critic_target"]).max() < 1e-6
+    assert np.abs(st.actor_target - ref["actor_target"]).max() < 1e-6
+    assert st.actor_iter == 1 and st.critic_iter == 1
+
+
+def test_ten_updates_track_autograd():
+    cfg = O.make_config(state_size=58, batch=32, hidden=(64, 48, 32, 16))
+    st = make_state(cfg, 3, "warm")
+    ref = to64(st)
+    rng = np.random.default_rng(5)
+    for i in range(10):
+        batch = O.synth_batch(cfg, rng, p_term=0.2)
+        ref, dia = R.update(cfg, ref, *batch)
+        loss, avgq = st.update(*batch)
+        assert abs(loss - dia["critic_loss"]) <= 1e-3 * abs(dia["critic_loss"]) + 1e-6, i
+        assert abs(avgq - dia["avg_q"]) <= 1e-3 * abs(dia["avg_q"]) + 1e-5, i
+    assert np.abs(st.critic - ref["critic"]).max() < 5e-4
+    assert np.abs(st.actor - ref["actor"]).max() < 5e-6
+    assert np.abs(st.critic_target - ref["critic_target"]).max() < 1e-5
+
+
+def test_edge_all_terminal_and_none_terminal():
+    cfg = O.make_config(state_size=58, batch=8, hidden=(32, 16, 16, 8))
+    for p in (0.0, 1.0):
+        st = make_state(cfg, 1, "warm")
+        rng = np.random.default_rng(2)
+        s, a, r, mc, term, sn = O.synth_batch(cfg, rng)
+        term[:] = 1 if p == 1.0 else 0
+        ref, dia = R.update(cfg, to64(st), s, a, r, mc, term, sn)
+        st.update(s, a, r, mc, term, sn, taps=True)
+        assert relerr(st.last_taps["y"], dia["y"]) < 1e-6
+        if p == 1.0:  # dqn.cpp:894: terminal => target ignores the target nets entirely
+            np.testing.assert_allclose(st.last_taps["y"], (0.5 * mc + 0.5 * r).astype(np.float32), rtol=1e-6)
+
+
+def test_clip_active_and_inactive():
+    cfg = O.make_config(state_size=58, batch=16, hidden=(32, 16, 16, 8))
+    rng = np.random.default_rng(9)
+    for mode, expect_clip in (("caffe", False), ("warm", True)):
+        st = make_state(cfg, 4, mode)
+        s, a, r, mc, term, sn = O.synth_batch(cfg, np.random.default_rng(10))
+        ref, dia = R.update(cfg, to64(st), s, a, r, mc, term, sn)
+        st.update(s, a, r, mc, term, sn, taps=True)
+        assert (st.last_taps["critic_gnorm"][0] > cfg.clip_gradients) == expect_clip
+        assert relerr(st.critic_m, ref["critic_m"]) < 1e-4
+
+
+def test_inverting_gradients_negative_factor():
+    # dqn.cpp:927-957: no clamping => factor goes negative when the output is outside its bounds
+    a = np.zeros((1, 10), np.float32); d = np.ones((1, 10), np.float32)
+    a[0, 0] = -3.0   # logit below min=-1, diff>0  -> (x-min)/(max-min) = -1
+    a[0, 4] = 150.0  # dash power above max=100
+    d[0, 4] = -2.0   # diff<0 -> (max-x)/(max-min) = -0.5 -> +1.0
+    out = O.invert_gradients(a, d)
+    assert out[0, 0] == pytest.approx(-1.0)
+    assert out[0, 4] == pytest.approx(1.0)
+    assert out[0, 1] == pytest.approx(0.5)         # x=0 in [-1,1], d>0
+    assert out[0, 5] == pytest.approx(0.5)         # angle 0 in [-180,180]
+    assert out[0, 8] == pytest.approx(0.0)         # kick power 0 in [0,100], d>0 -> 0
+
+
+def test_soft_update_freq_gt_one():
+    cfg = O.make_config(state_size=58, batch=8, hidden=(16, 16, 8, 8), soft_update_freq=2)
+    st = make_state(cfg, 4, "warm")
+    t0 = st.critic_target.copy()
+    rng = np.random.default_rng(1)
+    st.update(*O.synth_batch(cfg, rng))
+    assert np.array_equal(st.critic_target, t0)       # iter 1 % 2 != 0
+    st.update(*O.synth_batch(cfg, rng))
+    assert not np.array_equal(st.critic_target, t0)   # iter 2 % 2 == 0
+
+
+def test_label_transitions_and_replay_sizes_and_get_action():
+    r = np.array([0.1, -0.2, 0.3, 5.0], np.float32)
+    mc = O.label_transitions(r, 0.99)
+    exp = np.zeros(4); exp[3] = 5.0
+    for i in (2, 1, 0):
+        exp[i] = np.float32(np.float64(r[i]) + 0.99 * np.float64(np.float32(exp[i + 1])))
+    np.testing.assert_array_equal(mc, exp.astype(np.float32))
+    import ctypes as C
+    ns = C.c_int32()
+    L = O.lib()
+    assert L.dqo_replay_after_add_one(5, 5, C.byref(ns)) == 1 and ns.value == 5
+    assert L.dqo_replay_after_add_one(4, 5, C.byref(ns)) == 0 and ns.value == 5
+    # AddTransitions caps at capacity-1 (dqn.cpp:776: '>=')
+    assert L.dqo_replay_after_add_many(3, 5, 2, C.byref(ns)) == 1 and ns.value == 4
+    assert L.dqo_replay_after_add_many(0, 100, 10, C.byref(ns)) == 0 and ns.value == 10
+    # GetAction: tackle masked, first max wins, param offsets dqn.cpp:162-178
+    o = np.array([0.1, 0.5, 9.0, 0.5, 10, 20, 30, 40, 50, 60], np.float32)
+    assert O.get_action(o) == (1, 30.0, 0.0)
+    o[3] = 0.6
+    assert O.get_action(o) == (3, 50.0, 60.0)
+    o[0] = 0.7
+    assert O.get_action(o) == (0, 10.0, 20.0)
