@@ -1,0 +1,1260 @@
+// engine.cu — host side of libdqn_b200.so: owns the HBM-resident state of one dqn::DQN
+// (reference src/dqn.hpp:183-193: replay memory, 4 nets, 2 solvers) and sequences the kernels of
+// UpdateActorCritic (src/dqn.cpp:828-972) / SelectActionGreedily (:734-766) / CriticForward
+// (:982-1020) on CUDA streams, replaying one captured CUDA graph per update.
+#include "../../include/dqn_b200.h"
+
+#include <dlfcn.h>
+#include <string.h>
+
+#include <algorithm>
+#include <random>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "gemm.cuh"
+#include "kernels.cuh"
+
+namespace dqnb {
+
+std::string &last_error() {
+  static thread_local std::string e;
+  return e;
+}
+
+// ---------------------------------------------------------------------------------------------
+// driver entry point for TMA descriptors (no link-time libcuda dependency)
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
+                                  const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// Split-plane matrix [2][rows][ld] -> 3-D tensor map {ld (inner), rows, 2 planes}, fp32,
+// 128-byte swizzle, box {32, box_rows, 2}; out-of-bounds elements read as zero.
+static int make_tmap(CUtensorMap *tm, const float *base, int rows, int ld, long long plane_elems,
+                     int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) DQNB_FAIL("cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[3] = {(cuuint64_t)ld, (cuuint64_t)rows, 2};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 4ull, (cuuint64_t)plane_elems * 4ull};
+  cuuint32_t box[3] = {32, (cuuint32_t)box_rows, 2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)base, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) DQNB_FAIL("cuTensorMapEncodeTiled failed with CUresult %d (rows=%d ld=%d)", (int)r, rows, ld);
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// NCCL through dlopen (only when world_size > 1)
+// ---------------------------------------------------------------------------------------------
+struct Id128 { char b[128]; };
+struct NcclApi {
+  void *lib = nullptr;
+  int (*GetUniqueId)(void *) = nullptr;
+  int (*CommInitRank)(void **, int, /*ncclUniqueId by value: 128 bytes*/ Id128, int) = nullptr;
+  int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void *) = nullptr;
+  const char *(*GetErrorString)(int) = nullptr;
+};
+static NcclApi &nccl() {
+  static NcclApi api;
+  if (!api.lib) {
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *n : names) {
+      api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+      if (api.lib) break;
+    }
+    if (api.lib) {
+      api.GetUniqueId = (int (*)(void *))dlsym(api.lib, "ncclGetUniqueId");
+      api.CommInitRank = (int (*)(void **, int, Id128, int))dlsym(api.lib, "ncclCommInitRank");
+      api.AllReduce = (int (*)(const void *, void *, size_t, int, int, void *, cudaStream_t))dlsym(api.lib, "ncclAllReduce");
+      api.CommDestroy = (int (*)(void *))dlsym(api.lib, "ncclCommDestroy");
+      api.GetErrorString = (const char *(*)(int))dlsym(api.lib, "ncclGetErrorString");
+    }
+  }
+  return api;
+}
+constexpr int kNcclFloat = 7, kNcclSum = 0;
+
+// ---------------------------------------------------------------------------------------------
+// net geometry: Caffe-order blobs <-> padded internal flat layout
+// ---------------------------------------------------------------------------------------------
+struct LayerGeom {
+  int n_real, k_real;     // Caffe blob W [n_real x k_real]
+  int Np, Kp;             // padded
+  long long w_off, b_off; // internal offsets
+  long long cw_off, cb_off;  // Caffe-order offsets
+};
+struct NetGeom {
+  bool critic;
+  int n_hidden;
+  LayerGeom L[DQNB_MAX_HIDDEN];
+  int head_real;          // 10 (actor: action_layer 4 + actionpara_layer 6) or 1 (q_values_layer)
+  int Hp;                 // padded width of the top tower layer
+  long long hw_off, hb_off;   // internal: head W [16 x Hp], b [16]
+  long long chw_off[2], chb_off[2];
+  long long flat;         // internal element count (multiple of 1024)
+  long long caffe_count;
+  int in_real, in_pad;
+};
+
+static void make_geom(const dqnb_config &c, bool critic, NetGeom *g) {
+  memset(g, 0, sizeof(*g));
+  g->critic = critic;
+  g->n_hidden = c.n_hidden;
+  g->in_real = c.state_size + (critic ? kActorOut : 0);
+  g->in_pad = round_up(g->in_real, 64);
+  long long off = 0, coff = 0;
+  int k_real = g->in_real, Kp = g->in_pad;
+  for (int l = 0; l < c.n_hidden; ++l) {
+    LayerGeom &L = g->L[l];
+    L.n_real = c.hidden[l]; L.k_real = k_real;
+    L.Np = round_up(c.hidden[l], 64); L.Kp = Kp;
+    L.w_off = off; off += (long long)L.Np * L.Kp;
+    L.b_off = off; off += L.Np;
+    L.cw_off = coff; coff += (long long)L.n_real * L.k_real;
+    L.cb_off = coff; coff += L.n_real;
+    k_real = L.n_real; Kp = L.Np;
+  }
+  g->Hp = Kp;
+  g->head_real = critic ? 1 : kActorOut;
+  g->hw_off = off; off += 16LL * Kp;
+  g->hb_off = off; off += 16;
+  if (critic) {
+    g->chw_off[0] = coff; coff += k_real;
+    g->chb_off[0] = coff; coff += 1;
+  } else {
+    g->chw_off[0] = coff; coff += 4LL * k_real;
+    g->chb_off[0] = coff; coff += 4;
+    g->chw_off[1] = coff; coff += 6LL * k_real;
+    g->chb_off[1] = coff; coff += 6;
+  }
+  g->flat = (off + 1023) / 1024 * 1024;
+  g->caffe_count = coff;
+}
+
+// Caffe order -> internal padded (zero padding); head rows: actor = action_layer rows 0..3 then
+// actionpara_layer rows 4..9 of one [16 x Hp] matrix.
+static void caffe_to_internal(const NetGeom &g, const float *c, std::vector<float> &out) {
+  out.assign((size_t)g.flat, 0.f);
+  for (int l = 0; l < g.n_hidden; ++l) {
+    const LayerGeom &L = g.L[l];
+    for (int n = 0; n < L.n_real; ++n) {
+      memcpy(&out[L.w_off + (long long)n * L.Kp], c + L.cw_off + (long long)n * L.k_real, sizeof(float) * L.k_real);
+      out[L.b_off + n] = c[L.cb_off + n];
+    }
+  }
+  const int k_real = g.L[g.n_hidden - 1].n_real;
+  if (g.critic) {
+    memcpy(&out[g.hw_off], c + g.chw_off[0], sizeof(float) * k_real);
+    out[g.hb_off] = c[g.chb_off[0]];
+  } else {
+    for (int j = 0; j < 4; ++j) {
+      memcpy(&out[g.hw_off + (long long)j * g.Hp], c + g.chw_off[0] + (long long)j * k_real, sizeof(float) * k_real);
+      out[g.hb_off + j] = c[g.chb_off[0] + j];
+    }
+    for (int j = 0; j < 6; ++j) {
+      memcpy(&out[g.hw_off + (long long)(4 + j) * g.Hp], c + g.chw_off[1] + (long long)j * k_real, sizeof(float) * k_real);
+      out[g.hb_off + 4 + j] = c[g.chb_off[1] + j];
+    }
+  }
+}
+static void internal_to_caffe(const NetGeom &g, const float *in, float *c) {
+  for (int l = 0; l < g.n_hidden; ++l) {
+    const LayerGeom &L = g.L[l];
+    for (int n = 0; n < L.n_real; ++n) {
+      memcpy(c + L.cw_off + (long long)n * L.k_real, in + L.w_off + (long long)n * L.Kp, sizeof(float) * L.k_real);
+      c[L.cb_off + n] = in[L.b_off + n];
+    }
+  }
+  const int k_real = g.L[g.n_hidden - 1].n_real;
+  if (g.critic) {
+    memcpy(c + g.chw_off[0], in + g.hw_off, sizeof(float) * k_real);
+    c[g.chb_off[0]] = in[g.hb_off];
+  } else {
+    for (int j = 0; j < 4; ++j) {
+      memcpy(c + g.chw_off[0] + (long long)j * k_real, in + g.hw_off + (long long)j * g.Hp, sizeof(float) * k_real);
+      c[g.chb_off[0] + j] = in[g.hb_off + j];
+    }
+    for (int j = 0; j < 6; ++j) {
+      memcpy(c + g.chw_off[1] + (long long)j * k_real, in + g.hw_off + (long long)(4 + j) * g.Hp, sizeof(float) * k_real);
+      c[g.chb_off[1] + j] = in[g.hb_off + 4 + j];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+struct SplitMat {           // [2][rows][ld] fp32 in HBM
+  float *p = nullptr;
+  int rows = 0, ld = 0;
+  long long plane() const { return (long long)rows * ld; }
+};
+
+struct Op {                 // one kernel launch of the update / act sequence
+  enum Kind { GEMM, GATHER, SAMPLE, HEAD_FWD, QK, HEAD_BWD_X, HEAD_BWD_W, COLSUM, INVERT, REDUCE,
+              ALLREDUCE, ADAM, PREP, FINALIZE } kind;
+  GemmArgs gemm; dim3 grid;
+  GatherArgs gather; HeadArgs head; QArgs q; HeadBwdXArgs hbx; HeadBwdWArgs hbw; ColsumArgs cs;
+  InvertArgs inv; ReduceArgs red; AdamArgs adam;
+  float *ar_buf = nullptr; size_t ar_count = 0;
+  int blocks = 0;
+};
+
+}  // namespace dqnb
+
+using namespace dqnb;
+
+struct dqnb_handle_s {
+  dqnb_config cfg;
+  int S, Sp, Kc, B, Bp, An /*act rows pad*/;
+  NetGeom gA, gC;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::vector<void *> allocs;
+  std::vector<void *> pinned;
+  // params: [2][flat]
+  float *P[4] = {nullptr, nullptr, nullptr, nullptr};
+  float *Mo[2] = {nullptr, nullptr}, *Vo[2] = {nullptr, nullptr};
+  float *G[2] = {nullptr, nullptr};   // reduced gradients [flat + 4]
+  float *Gpart[2] = {nullptr, nullptr}; long long gpart_stride[2] = {0, 0};   // [actor, critic]
+  float *norm_part = nullptr; int n_norm[2] = {0, 0};
+  double *scal_part = nullptr; int n_scal = 0;
+  // replay ring
+  float *ring_s = nullptr, *ring_sn = nullptr, *ring_misc = nullptr;
+  int ring_head = 0, ring_size = 0;
+  // minibatch buffers
+  int32_t *idx = nullptr;
+  SplitMat Xs, Xsn, Xc, Xct, Xcp;
+  float *reward = nullptr, *mc = nullptr, *term = nullptr, *y = nullptr;
+  float *q_next = nullptr, *q = nullptr, *q_pi = nullptr;
+  float *q16 = nullptr, *a16_t = nullptr, *a16_pi = nullptr, *d16c = nullptr, *d16a = nullptr;
+  float *d_in = nullptr, *tap_raw = nullptr, *tap_inv = nullptr;
+  SplitMat actAT[DQNB_MAX_HIDDEN], actCT[DQNB_MAX_HIDDEN], actC[DQNB_MAX_HIDDEN], actA[DQNB_MAX_HIDDEN], dZ[DQNB_MAX_HIDDEN];
+  // act path
+  SplitMat Xact, Xeval, actE[DQNB_MAX_HIDDEN];
+  float *out16_act = nullptr;
+  float *h_act_in = nullptr, *h_act_out = nullptr;   // pinned staging
+  // step state / results
+  StepState *st = nullptr;
+  float *results = nullptr; int max_slots = 4096;
+  float *h_results = nullptr;
+  // staging for replay appends
+  float *h_stage_s = nullptr, *h_stage_sn = nullptr, *h_stage_misc = nullptr; int stage_rows = 0;
+  // op lists + graphs
+  std::vector<Op> update_ops, act_ops, eval_ops;
+  cudaGraphExec_t graph_sampled = nullptr, graph_injected = nullptr;
+  int kernels_per_update_sampled = 0, kernels_per_update_injected = 0;
+  int64_t launches = 0;
+  void *comm = nullptr;
+  HyperParams hp;
+  SegTable segs[2];
+};
+
+namespace dqnb {
+
+template <typename T>
+static int dalloc(dqnb_handle_s *h, T **p, size_t count, bool zero = true) {
+  void *d = nullptr;
+  DQNB_CUDA(cudaMalloc(&d, count * sizeof(T)));
+  if (zero) DQNB_CUDA(cudaMemset(d, 0, count * sizeof(T)));
+  h->allocs.push_back(d);
+  *p = (T *)d;
+  return 0;
+}
+template <typename T>
+static int halloc(dqnb_handle_s *h, T **p, size_t count) {
+  void *d = nullptr;
+  DQNB_CUDA(cudaMallocHost(&d, count * sizeof(T)));
+  memset(d, 0, count * sizeof(T));
+  h->pinned.push_back(d);
+  *p = (T *)d;
+  return 0;
+}
+static int alloc_mat(dqnb_handle_s *h, SplitMat *m, int rows, int ld) {
+  m->rows = rows; m->ld = ld;
+  return dalloc(h, &m->p, (size_t)2 * rows * ld);
+}
+
+// ---------------------------------------------------------------------------------------------
+// GEMM op builders
+// ---------------------------------------------------------------------------------------------
+static int pick_splits(int tiles, int kblocks, int max_splits) {
+  int s = 1;
+  while (s * 2 <= max_splits && tiles * s * 2 <= 160 && kblocks / (s * 2) >= 2) s *= 2;
+  return s;
+}
+
+static int finish_gemm(const dqnb_config &cfg, Op *op) {
+  GemmParams &p = op->gemm.p;
+  op->kind = Op::GEMM;
+  if (cfg.gemm_mode == DQNB_GEMM_TCGEN05_3XTF32) {
+    // A
+    const int a_rows = p.a_mn ? p.K : p.M, b_rows = p.b_mn ? p.K : p.N;
+    if (make_tmap(&op->gemm.tmA, p.A, a_rows, p.lda, p.a_plane, p.a_mn ? 32 : BM)) return -1;
+    if (make_tmap(&op->gemm.tmB, p.B, b_rows, p.ldb, p.b_plane, p.b_mn ? 32 : BN)) return -1;
+    op->grid = dim3((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, p.splits);
+  } else {
+    op->grid = dim3((p.N + ST - 1) / ST, (p.M + ST - 1) / ST, p.splits);
+  }
+  return 0;
+}
+
+// forward of tower layer l: H = lrelu(X W^T + b)
+static int op_fwd(const dqnb_config &cfg, const NetGeom &g, int l, const float *P, const SplitMat &X,
+                  const SplitMat &H, Op *op) {
+  const LayerGeom &L = g.L[l];
+  GemmParams &p = op->gemm.p;
+  memset(&p, 0, sizeof(p));
+  p.M = X.rows; p.N = L.Np; p.K = L.Kp; p.a_mn = 0; p.b_mn = 0; p.splits = 1; p.epi = EPI_FWD;
+  p.A = X.p; p.a_plane = X.plane(); p.lda = X.ld;
+  p.B = P + L.w_off; p.b_plane = g.flat; p.ldb = L.Kp;
+  p.out_hi = H.p; p.out_lo = H.p + H.plane(); p.ldo = H.ld;
+  p.bias_hi = P + L.b_off; p.bias_lo = P + g.flat + L.b_off; p.apply_lrelu = 1;
+  return finish_gemm(cfg, op);
+}
+// backward w.r.t. bottom of layer l (l >= 1): dZ_{l-1} = (dZ_l W_l) * relu'(H_{l-1})
+static int op_dx(const dqnb_config &cfg, const NetGeom &g, int l, const float *P, const SplitMat &dZl,
+                 const SplitMat &Hprev, const SplitMat &dZprev, Op *op) {
+  const LayerGeom &L = g.L[l];
+  GemmParams &p = op->gemm.p;
+  memset(&p, 0, sizeof(p));
+  p.M = dZl.rows; p.N = L.Kp; p.K = L.Np; p.a_mn = 0; p.b_mn = 1; p.splits = 1; p.epi = EPI_DX;
+  p.A = dZl.p; p.a_plane = dZl.plane(); p.lda = dZl.ld;
+  p.B = P + L.w_off; p.b_plane = g.flat; p.ldb = L.Kp;
+  p.out_hi = dZprev.p; p.out_lo = dZprev.p + dZprev.plane(); p.ldo = dZprev.ld;
+  p.mask_hi = Hprev.p; p.mask_lo = Hprev.p + Hprev.plane(); p.ldmask = Hprev.ld;
+  return finish_gemm(cfg, op);
+}
+// input diff of layer 0 (critic policy pass): d_in = dZ_0 W_0, raw fp32
+static int op_dx_plain(const dqnb_config &cfg, const NetGeom &g, const float *P, const SplitMat &dZ0,
+                       float *d_in, Op *op) {
+  const LayerGeom &L = g.L[0];
+  GemmParams &p = op->gemm.p;
+  memset(&p, 0, sizeof(p));
+  p.M = dZ0.rows; p.N = L.Kp; p.K = L.Np; p.a_mn = 0; p.b_mn = 1; p.splits = 1; p.epi = EPI_PLAIN;
+  p.A = dZ0.p; p.a_plane = dZ0.plane(); p.lda = dZ0.ld;
+  p.B = P + L.w_off; p.b_plane = g.flat; p.ldb = L.Kp;
+  p.out = d_in; p.out_split_stride = 0; p.ldo = L.Kp;
+  return finish_gemm(cfg, op);
+}
+// weight gradient of layer l: dW_l = dZ_l^T X_{l-1} (contraction over the minibatch, split-K)
+static int op_dw(const dqnb_config &cfg, const NetGeom &g, int l, const SplitMat &dZl, const SplitMat &Xin,
+                 float *gpart, long long gpart_stride, int *splits_out, Op *op) {
+  const LayerGeom &L = g.L[l];
+  GemmParams &p = op->gemm.p;
+  memset(&p, 0, sizeof(p));
+  p.M = L.Np; p.N = L.Kp; p.K = dZl.rows; p.a_mn = 1; p.b_mn = 1; p.epi = EPI_PLAIN;
+  const int tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
+  p.splits = pick_splits(tiles, p.K / BK, kGradSplits);
+  *splits_out = p.splits;
+  p.A = dZl.p; p.a_plane = dZl.plane(); p.lda = dZl.ld;
+  p.B = Xin.p; p.b_plane = Xin.plane(); p.ldb = Xin.ld;
+  p.out = gpart + L.w_off; p.out_split_stride = gpart_stride; p.ldo = L.Kp;
+  return finish_gemm(cfg, op);
+}
+
+static void op_head_fwd(const NetGeom &g, const float *P, const SplitMat &H, int rows, float *out16,
+                        const SplitMat *dst, int dst_col, Op *op) {
+  op->kind = Op::HEAD_FWD;
+  HeadArgs &a = op->head;
+  memset(&a, 0, sizeof(a));
+  a.H = H.p; a.h_plane = H.plane(); a.ldh = H.ld; a.Kp = g.Hp;
+  a.W = P + g.hw_off; a.w_plane = g.flat; a.bias = P + g.hb_off; a.b_plane = g.flat;
+  a.J = g.head_real; a.rows = rows; a.out16 = out16;
+  if (dst) { a.dst = dst->p; a.dst_plane = dst->plane(); a.ldd = dst->ld; a.dst_col = dst_col; }
+  op->blocks = (rows + 7) / 8;
+}
+
+}  // namespace dqnb
+
+// ---------------------------------------------------------------------------------------------
+// launching
+// ---------------------------------------------------------------------------------------------
+static int launch_op(dqnb_handle_s *h, const Op &op, cudaStream_t s) {
+  switch (op.kind) {
+    case Op::GEMM:
+      if (h->cfg.gemm_mode == DQNB_GEMM_TCGEN05_3XTF32)
+        gemm_tc_kernel<<<op.grid, TC_THREADS, TC_SMEM_BYTES, s>>>(op.gemm);
+      else
+        gemm_simt_kernel<<<op.grid, 256, 0, s>>>(op.gemm.p);
+      break;
+    case Op::GATHER: gather_kernel<<<h->Bp, 128, 0, s>>>(op.gather); break;
+    case Op::SAMPLE: sample_kernel<<<(h->B + 255) / 256, 256, 0, s>>>(h->st, h->cfg.seed, h->B, h->idx); break;
+    case Op::HEAD_FWD: head_fwd_kernel<<<op.blocks, 256, 0, s>>>(op.head); break;
+    case Op::QK: q_kernel<<<op.blocks, 256, 0, s>>>(op.q); break;
+    case Op::HEAD_BWD_X: head_bwd_x_kernel<<<op.blocks, 256, 0, s>>>(op.hbx); break;
+    case Op::HEAD_BWD_W: head_bwd_w_kernel<<<op.grid, 512, 0, s>>>(op.hbw); break;
+    case Op::COLSUM: colsum_kernel<<<op.grid, 512, 0, s>>>(op.cs); break;
+    case Op::INVERT: invert_kernel<<<op.blocks, 256, 0, s>>>(op.inv); break;
+    case Op::REDUCE: reduce_kernel<<<op.blocks, 256, 0, s>>>(op.red); break;
+    case Op::ADAM: adam_kernel<<<op.blocks, 256, 0, s>>>(op.adam); break;
+    case Op::PREP: prep_kernel<<<1, 32, 0, s>>>(h->st, h->hp); break;
+    case Op::FINALIZE:
+      finalize_kernel<<<1, 32, 0, s>>>(h->st, h->G[1] + h->gC.flat, h->G[0] + h->gA.flat, h->results, h->max_slots);
+      break;
+    case Op::ALLREDUCE: {
+      if (!h->comm) DQNB_FAIL("world_size > 1 but dqnb_comm_init was not called");
+      int r = nccl().AllReduce(op.ar_buf, op.ar_buf, op.ar_count, kNcclFloat, kNcclSum, h->comm, s);
+      if (r != 0) DQNB_FAIL("ncclAllReduce failed: %s", nccl().GetErrorString ? nccl().GetErrorString(r) : "?");
+      return 0;
+    }
+  }
+  DQNB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int run_ops(dqnb_handle_s *h, const std::vector<Op> &ops, cudaStream_t s, bool skip_sample, int *count) {
+  int n = 0;
+  for (const Op &op : ops) {
+    if (skip_sample && op.kind == Op::SAMPLE) continue;
+    if (launch_op(h, op, s)) return -1;
+    if (op.kind != Op::ALLREDUCE) ++n;
+  }
+  if (count) *count = n;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// building the op lists
+// ---------------------------------------------------------------------------------------------
+static int build_forward(dqnb_handle_s *h, const NetGeom &g, const float *P, const SplitMat &X,
+                         SplitMat *acts, std::vector<Op> &ops) {
+  const SplitMat *in = &X;
+  for (int l = 0; l < g.n_hidden; ++l) {
+    Op op;
+    if (op_fwd(h->cfg, g, l, P, *in, acts[l], &op)) return -1;
+    ops.push_back(op);
+    in = &acts[l];
+  }
+  return 0;
+}
+
+// tower backward from dZ[top] (already masked): weight/bias gradient partials (optional) + dX chain
+static int build_backward(dqnb_handle_s *h, const NetGeom &g, const float *P, const SplitMat &X,
+                          SplitMat *acts, bool want_dw, SegTable *segs, std::vector<Op> &ops) {
+  const int top = g.n_hidden - 1;
+  for (int l = top; l >= 0; --l) {
+    if (l > 0) {
+      Op op;
+      if (op_dx(h->cfg, g, l, P, h->dZ[l], acts[l - 1], h->dZ[l - 1], &op)) return -1;
+      ops.push_back(op);
+    }
+    if (want_dw) {
+      Op op;
+      int splits = 1;
+      if (op_dw(h->cfg, g, l, h->dZ[l], l > 0 ? acts[l - 1] : X, h->Gpart[g.critic], h->gpart_stride[g.critic], &splits, &op)) return -1;
+      ops.push_back(op);
+      // segment table entries (internal flat order: W_l then b_l)
+      SegTable &T = *segs;
+      T.begin[2 * l] = g.L[l].w_off; T.end[2 * l] = g.L[l].b_off; T.nsplit[2 * l] = splits;
+      T.begin[2 * l + 1] = g.L[l].b_off; T.end[2 * l + 1] = g.L[l].b_off + g.L[l].Np; T.nsplit[2 * l + 1] = kGradSplits;
+    }
+  }
+  if (want_dw) {
+    Op op;
+    op.kind = Op::COLSUM;
+    ColsumArgs &a = op.cs;
+    memset(&a, 0, sizeof(a));
+    a.n_layers = g.n_hidden; a.rows_pad = h->Bp;
+    int blk = 0;
+    for (int l = 0; l < g.n_hidden; ++l) {
+      a.dZ[l] = h->dZ[l].p; a.plane[l] = h->dZ[l].plane(); a.ld[l] = h->dZ[l].ld; a.Np[l] = g.L[l].Np;
+      a.b_off[l] = g.L[l].b_off; a.blk_begin[l] = blk; blk += (g.L[l].Np + 127) / 128;
+    }
+    a.blk_begin[g.n_hidden] = blk;
+    a.gpart = h->Gpart[g.critic]; a.gpart_stride = h->gpart_stride[g.critic];
+    op.grid = dim3(blk, kGradSplits);
+    ops.push_back(op);
+    SegTable &T = *segs;
+    const int hs = 2 * g.n_hidden;
+    T.begin[hs] = g.hw_off; T.end[hs] = g.flat; T.nsplit[hs] = kGradSplits;   // head W, b (+ zero tail)
+    T.n = hs + 1;
+  }
+  return 0;
+}
+
+static void build_solver(dqnb_handle_s *h, int is_critic, const SegTable &segs, float scal_scale, std::vector<Op> &ops) {
+  const NetGeom &g = is_critic ? h->gC : h->gA;
+  const int blocks = (int)(g.flat / 1024);
+  const bool multi = h->cfg.world_size > 1;
+  Op r;
+  r.kind = Op::REDUCE;
+  ReduceArgs &a = r.red;
+  memset(&a, 0, sizeof(a));
+  a.segs = segs; a.flat = g.flat; a.gpart = h->Gpart[is_critic]; a.gpart_stride = h->gpart_stride[is_critic];
+  a.G = h->G[is_critic]; a.norm_part = h->norm_part; a.scal_part = h->scal_part; a.n_scal = h->n_scal;
+  a.scal_scale = scal_scale; a.do_reduce = 1; a.do_sumsq = multi ? 0 : 1;
+  r.blocks = blocks;
+  ops.push_back(r);
+  if (multi) {
+    Op ar;
+    ar.kind = Op::ALLREDUCE; ar.ar_buf = h->G[is_critic]; ar.ar_count = (size_t)g.flat + 4;
+    ops.push_back(ar);
+    Op r2 = r;
+    r2.red.do_reduce = 0; r2.red.do_sumsq = 1;
+    ops.push_back(r2);
+  }
+  Op ad;
+  ad.kind = Op::ADAM;
+  AdamArgs &d = ad.adam;
+  memset(&d, 0, sizeof(d));
+  d.flat = g.flat; d.G = h->G[is_critic]; d.norm_part = h->norm_part; d.n_norm = blocks;
+  d.M = h->Mo[is_critic]; d.V = h->Vo[is_critic];
+  d.P = h->P[is_critic ? DQNB_CRITIC : DQNB_ACTOR]; d.p_plane = g.flat;
+  d.T = h->P[is_critic ? DQNB_CRITIC_TARGET : DQNB_ACTOR_TARGET]; d.t_plane = g.flat;
+  d.st = h->st; d.st_out = h->st; d.is_critic = is_critic; d.hp = h->hp;
+  ad.blocks = blocks;
+  ops.push_back(ad);
+}
+
+static void push_q(dqnb_handle_s *h, int mode, float *q_tap, float *d16, std::vector<Op> &ops) {
+  Op op;
+  op.kind = Op::QK;
+  QArgs &a = op.q;
+  memset(&a, 0, sizeof(a));
+  a.mode = mode; a.B = h->B; a.q16 = h->q16; a.reward = h->reward; a.mc = h->mc; a.term = h->term;
+  a.y = h->y; a.q_tap = q_tap; a.d16 = d16; a.part = h->scal_part; a.hp = h->hp;
+  op.blocks = (h->B + 255) / 256;
+  ops.push_back(op);
+}
+static void push_head_bwd(dqnb_handle_s *h, const NetGeom &g, const float *P, const float *d16,
+                          const SplitMat &Htop, bool want_dw, std::vector<Op> &ops) {
+  const int top = g.n_hidden - 1;
+  Op x;
+  x.kind = Op::HEAD_BWD_X;
+  HeadBwdXArgs &a = x.hbx;
+  memset(&a, 0, sizeof(a));
+  a.d16 = d16; a.J = g.head_real; a.W = P + g.hw_off; a.w_plane = g.flat; a.Kp = g.Hp;
+  a.H = Htop.p; a.h_plane = Htop.plane(); a.ldh = Htop.ld;
+  a.dZ = h->dZ[top].p; a.dz_plane = h->dZ[top].plane(); a.rows_pad = h->Bp;
+  x.blocks = (int)(((long long)h->Bp * g.Hp + 255) / 256);
+  ops.push_back(x);
+  if (want_dw) {
+    Op w;
+    w.kind = Op::HEAD_BWD_W;
+    HeadBwdWArgs &b = w.hbw;
+    memset(&b, 0, sizeof(b));
+    b.d16 = d16; b.J = g.head_real; b.H = Htop.p; b.h_plane = Htop.plane(); b.ldh = Htop.ld; b.Kp = g.Hp;
+    b.rows_pad = h->Bp; b.gpart = h->Gpart[g.critic]; b.gpart_stride = h->gpart_stride[g.critic]; b.hw_off = g.hw_off; b.hb_off = g.hb_off;
+    w.grid = dim3((g.Hp + 127) / 128, kGradSplits);
+    ops.push_back(w);
+  }
+}
+
+static int build_update_ops(dqnb_handle_s *h) {
+  std::vector<Op> &ops = h->update_ops;
+  ops.clear();
+  const NetGeom &gA = h->gA, &gC = h->gC;
+  float *PA = h->P[DQNB_ACTOR], *PC = h->P[DQNB_CRITIC], *PAT = h->P[DQNB_ACTOR_TARGET], *PCT = h->P[DQNB_CRITIC_TARGET];
+  const int topA = gA.n_hidden - 1, topC = gC.n_hidden - 1;
+  Op op;
+  op.kind = Op::PREP; ops.push_back(op);
+  op.kind = Op::SAMPLE; ops.push_back(op);                       // dqn.cpp:846
+  op.kind = Op::GATHER;                                          // dqn.cpp:859-887
+  {
+    GatherArgs &a = op.gather;
+    memset(&a, 0, sizeof(a));
+    a.st = h->st; a.idx = h->idx; a.ring_s = h->ring_s; a.ring_sn = h->ring_sn; a.ring_misc = h->ring_misc;
+    a.cap = h->cfg.replay_capacity; a.B = h->B; a.Bp = h->Bp; a.S = h->S; a.Sp = h->Sp; a.Kc = h->Kc;
+    a.Xs = h->Xs.p; a.Xsn = h->Xsn.p; a.Xc = h->Xc.p; a.Xct = h->Xct.p; a.Xcp = h->Xcp.p;
+    a.reward = h->reward; a.mc = h->mc; a.term = h->term;
+  }
+  ops.push_back(op);
+  // dqn.cpp:889-891 CriticForwardThroughActor(critic_target, actor_target, s')
+  if (build_forward(h, gA, PAT, h->Xsn, h->actAT, ops)) return -1;
+  op_head_fwd(gA, PAT, h->actAT[topA], h->B, h->a16_t, &h->Xct, h->S, &op); ops.push_back(op);
+  if (build_forward(h, gC, PCT, h->Xct, h->actCT, ops)) return -1;
+  op_head_fwd(gC, PCT, h->actCT[topC], h->B, h->q16, nullptr, 0, &op); ops.push_back(op);
+  push_q(h, QMODE_TARGET, h->q_next, nullptr, ops);              // dqn.cpp:892-900
+  // dqn.cpp:904 critic_solver_->Step(1)
+  if (build_forward(h, gC, PC, h->Xc, h->actC, ops)) return -1;
+  op_head_fwd(gC, PC, h->actC[topC], h->B, h->q16, nullptr, 0, &op); ops.push_back(op);
+  push_q(h, QMODE_LOSS, h->q, h->d16c, ops);
+  push_head_bwd(h, gC, PC, h->d16c, h->actC[topC], true, ops);
+  if (build_backward(h, gC, PC, h->Xc, h->actC, true, &h->segs[1], ops)) return -1;
+  build_solver(h, 1, h->segs[1], 0.5f * h->hp.inv_batch_global, ops);
+  // dqn.cpp:910-916 actor forward, critic forward with the updated critic
+  if (build_forward(h, gA, PA, h->Xs, h->actA, ops)) return -1;
+  op_head_fwd(gA, PA, h->actA[topA], h->B, h->a16_pi, &h->Xcp, h->S, &op); ops.push_back(op);
+  if (build_forward(h, gC, PC, h->Xcp, h->actC, ops)) return -1;
+  op_head_fwd(gC, PC, h->actC[topC], h->B, h->q16, nullptr, 0, &op); ops.push_back(op);
+  push_q(h, QMODE_POLICY, h->q_pi, h->d16c, ops);                // dqn.cpp:918-921
+  // dqn.cpp:923 critic.BackwardFrom(q_values_layer): only the input diff is consumed
+  push_head_bwd(h, gC, PC, h->d16c, h->actC[topC], false, ops);
+  if (build_backward(h, gC, PC, h->Xcp, h->actC, false, nullptr, ops)) return -1;
+  if (op_dx_plain(h->cfg, gC, PC, h->dZ[0], h->d_in, &op)) return -1;
+  ops.push_back(op);
+  op.kind = Op::INVERT;                                          // dqn.cpp:927-957
+  {
+    InvertArgs &a = op.inv;
+    memset(&a, 0, sizeof(a));
+    a.B = h->B; a.Bp = h->Bp; a.S = h->S; a.ldin = h->Kc; a.d_in = h->d_in; a.a16 = h->a16_pi; a.d16 = h->d16a;
+    a.tap_raw = h->tap_raw; a.tap_inv = h->tap_inv;
+    op.blocks = (h->Bp * 16 + 255) / 256;
+  }
+  ops.push_back(op);
+  // dqn.cpp:960-965 actor backward + ApplyUpdate
+  push_head_bwd(h, gA, PA, h->d16a, h->actA[topA], true, ops);
+  if (build_backward(h, gA, PA, h->Xs, h->actA, true, &h->segs[0], ops)) return -1;
+  build_solver(h, 0, h->segs[0], h->hp.inv_batch_global, ops);
+  op.kind = Op::FINALIZE; ops.push_back(op);
+  return 0;
+}
+
+static int build_act_ops(dqnb_handle_s *h) {
+  Op op;
+  h->act_ops.clear();
+  if (build_forward(h, h->gA, h->P[DQNB_ACTOR], h->Xact, h->actE, h->act_ops)) return -1;
+  op_head_fwd(h->gA, h->P[DQNB_ACTOR], h->actE[h->gA.n_hidden - 1], h->An, h->out16_act, nullptr, 0, &op);
+  h->act_ops.push_back(op);
+  h->eval_ops.clear();
+  if (build_forward(h, h->gC, h->P[DQNB_CRITIC], h->Xeval, h->actE, h->eval_ops)) return -1;
+  op_head_fwd(h->gC, h->P[DQNB_CRITIC], h->actE[h->gC.n_hidden - 1], h->An, h->out16_act, nullptr, 0, &op);
+  h->eval_ops.push_back(op);
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// C-ABI
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+const char *dqnb_last_error(void) { return last_error().c_str(); }
+const char *dqnb_version(void) { return "dqn_b200 0.1 (sm_100a; tcgen05 3xTF32 + TMA + TMEM)"; }
+
+void dqnb_default_config(dqnb_config *c) {
+  memset(c, 0, sizeof(*c));
+  c->struct_size = (int32_t)sizeof(*c);
+  c->device = 0;
+  c->state_size = 58;
+  c->batch = 32;
+  c->n_hidden = 4;
+  const int hid[4] = {1024, 512, 256, 128};
+  for (int i = 0; i < 4; ++i) c->hidden[i] = hid[i];
+  c->replay_capacity = 500000;
+  c->max_act_batch = 32;
+  c->gamma = 0.99; c->beta = 0.5; c->tau = 0.001f; c->soft_update_freq = 1;
+  c->actor_lr = 1e-5f; c->critic_lr = 1e-3f; c->momentum = 0.95f; c->momentum2 = 0.999f;
+  c->delta = 1e-8f; c->clip_gradients = 10.f;
+  c->seed = 1; c->gemm_mode = DQNB_GEMM_TCGEN05_3XTF32; c->use_graph = 1; c->world_size = 1; c->rank = 0;
+}
+
+int dqnb_destroy(dqnb_handle h) {
+  if (!h) return 0;
+  cudaSetDevice(h->cfg.device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->graph_sampled) cudaGraphExecDestroy(h->graph_sampled);
+  if (h->graph_injected) cudaGraphExecDestroy(h->graph_injected);
+  if (h->comm && nccl().CommDestroy) nccl().CommDestroy(h->comm);
+  for (void *p : h->allocs) cudaFree(p);
+  for (void *p : h->pinned) cudaFreeHost(p);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return 0;
+}
+
+static int create_impl(const dqnb_config *cfg, dqnb_handle_s *h) {
+  h->cfg = *cfg;
+  const dqnb_config &c = h->cfg;
+  if (c.struct_size != (int32_t)sizeof(dqnb_config)) DQNB_FAIL("dqnb_config.struct_size mismatch (%d vs %d)", c.struct_size, (int)sizeof(dqnb_config));
+  if (c.state_size <= 0 || c.batch <= 0 || c.n_hidden < 1 || c.n_hidden > DQNB_MAX_HIDDEN) DQNB_FAIL("bad dimensions");
+  for (int l = 0; l < c.n_hidden; ++l) if (c.hidden[l] <= 0) DQNB_FAIL("bad hidden size");
+  if (c.replay_capacity < 2) DQNB_FAIL("replay_capacity must be >= 2");
+  if (c.world_size < 1 || c.rank < 0 || c.rank >= c.world_size) DQNB_FAIL("bad world_size/rank");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    DQNB_FAIL("no CUDA device: libdqn_b200 has no CPU fallback");
+  if (c.device < 0 || c.device >= ndev) DQNB_FAIL("device %d out of range (%d devices)", c.device, ndev);
+  cudaDeviceProp prop;
+  DQNB_CUDA(cudaGetDeviceProperties(&prop, c.device));
+  if (prop.major != 10) DQNB_FAIL("device %d is sm_%d%d; this library is built for sm_100a only", c.device, prop.major, prop.minor);
+  DQNB_CUDA(cudaSetDevice(c.device));
+  DQNB_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  DQNB_CUDA(cudaEventCreate(&h->ev0));
+  DQNB_CUDA(cudaEventCreate(&h->ev1));
+  DQNB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+
+  h->S = c.state_size; h->Sp = round_up(c.state_size, 64); h->Kc = round_up(c.state_size + kActorOut, 64);
+  h->B = c.batch; h->Bp = round_up(c.batch, 128);
+  h->An = round_up(std::max(1, c.max_act_batch), 128);
+  make_geom(c, false, &h->gA);
+  make_geom(c, true, &h->gC);
+  h->hp.gamma = c.gamma; h->hp.beta = c.beta; h->hp.tau = c.tau; h->hp.soft_update_freq = c.soft_update_freq;
+  h->hp.actor_lr = c.actor_lr; h->hp.critic_lr = c.critic_lr; h->hp.beta1 = c.momentum; h->hp.beta2 = c.momentum2;
+  h->hp.eps = c.delta; h->hp.clip = c.clip_gradients;
+  h->hp.inv_batch_global = 1.f / (float)(c.batch * c.world_size);
+
+  const long long fA = h->gA.flat, fC = h->gC.flat, fmax = std::max(fA, fC);
+  for (int n = 0; n < 4; ++n) if (dalloc(h, &h->P[n], (size_t)2 * ((n & 1) ? fC : fA))) return -1;
+  if (dalloc(h, &h->Mo[0], fA) || dalloc(h, &h->Vo[0], fA) || dalloc(h, &h->Mo[1], fC) || dalloc(h, &h->Vo[1], fC)) return -1;
+  if (dalloc(h, &h->G[0], fA + 4) || dalloc(h, &h->G[1], fC + 4)) return -1;
+  h->gpart_stride[0] = fA; h->gpart_stride[1] = fC;
+  if (dalloc(h, &h->Gpart[0], (size_t)kGradSplits * fA) || dalloc(h, &h->Gpart[1], (size_t)kGradSplits * fC)) return -1;
+  if (dalloc(h, &h->norm_part, (size_t)(fmax / 1024))) return -1;
+  h->n_scal = (h->B + 255) / 256;
+  if (dalloc(h, &h->scal_part, (size_t)h->n_scal)) return -1;
+  // replay ring (rows padded to Sp floats = 256 B multiples: aligned, vectorisable gathers)
+  const size_t cap = (size_t)c.replay_capacity;
+  if (dalloc(h, &h->ring_s, cap * h->Sp) || dalloc(h, &h->ring_sn, cap * h->Sp) || dalloc(h, &h->ring_misc, cap * kMiscStride)) return -1;
+  if (dalloc(h, &h->idx, (size_t)h->Bp)) return -1;
+  if (alloc_mat(h, &h->Xs, h->Bp, h->Sp) || alloc_mat(h, &h->Xsn, h->Bp, h->Sp) || alloc_mat(h, &h->Xc, h->Bp, h->Kc) ||
+      alloc_mat(h, &h->Xct, h->Bp, h->Kc) || alloc_mat(h, &h->Xcp, h->Bp, h->Kc)) return -1;
+  float **vecs[] = {&h->reward, &h->mc, &h->term, &h->y, &h->q_next, &h->q, &h->q_pi};
+  for (float **v : vecs) if (dalloc(h, v, (size_t)h->Bp)) return -1;
+  const int rows16 = std::max(h->Bp, h->An);
+  float **m16[] = {&h->q16, &h->a16_t, &h->a16_pi, &h->d16c, &h->d16a, &h->out16_act};
+  for (float **v : m16) if (dalloc(h, v, (size_t)rows16 * 16)) return -1;
+  if (dalloc(h, &h->d_in, (size_t)h->Bp * h->Kc) || dalloc(h, &h->tap_raw, (size_t)h->Bp * kActorOut) || dalloc(h, &h->tap_inv, (size_t)h->Bp * kActorOut)) return -1;
+  for (int l = 0; l < c.n_hidden; ++l) {
+    const int Np = h->gA.L[l].Np;
+    if (alloc_mat(h, &h->actAT[l], h->Bp, Np) || alloc_mat(h, &h->actCT[l], h->Bp, Np) || alloc_mat(h, &h->actC[l], h->Bp, Np) ||
+        alloc_mat(h, &h->actA[l], h->Bp, Np) || alloc_mat(h, &h->dZ[l], h->Bp, Np) || alloc_mat(h, &h->actE[l], h->An, Np)) return -1;
+  }
+  if (alloc_mat(h, &h->Xact, h->An, h->Sp) || alloc_mat(h, &h->Xeval, h->An, h->Kc)) return -1;
+  if (halloc(h, &h->h_act_in, (size_t)2 * h->An * h->Kc) || halloc(h, &h->h_act_out, (size_t)h->An * 16)) return -1;
+  if (dalloc(h, &h->st, 1) || dalloc(h, &h->results, (size_t)2 * h->max_slots)) return -1;
+  if (halloc(h, &h->h_results, (size_t)2 * h->max_slots)) return -1;
+  h->stage_rows = 4096;
+  if (halloc(h, &h->h_stage_s, (size_t)h->stage_rows * h->Sp) || halloc(h, &h->h_stage_sn, (size_t)h->stage_rows * h->Sp) ||
+      halloc(h, &h->h_stage_misc, (size_t)h->stage_rows * kMiscStride)) return -1;
+  if (build_update_ops(h) || build_act_ops(h)) return -1;
+  DQNB_CUDA(cudaStreamSynchronize(h->stream));
+  DQNB_CUDA(cudaDeviceSynchronize());
+  return 0;
+}
+
+int dqnb_create(const dqnb_config *cfg, dqnb_handle *out) {
+  if (!cfg || !out) DQNB_FAIL("null argument");
+  dqnb_handle_s *h = new dqnb_handle_s();
+  if (create_impl(cfg, h)) {
+    std::string keep = last_error();
+    dqnb_destroy(h);
+    last_error() = keep;
+    *out = nullptr;
+    return -1;
+  }
+  *out = h;
+  return 0;
+}
+
+int64_t dqnb_param_count(dqnb_handle h, int net) {
+  if (!h || net < 0 || net > 3) return -1;
+  return (net & 1) ? h->gC.caffe_count : h->gA.caffe_count;
+}
+
+int dqnb_set_params(dqnb_handle h, int net, const float *params) {
+  if (!h || net < 0 || net > 3 || !params) DQNB_FAIL("bad argument");
+  DQNB_CUDA(cudaSetDevice(h->cfg.device));
+  const NetGeom &g = (net & 1) ? h->gC : h->gA;
+  std::vector<float> in;
+  caffe_to_internal(g, params, in);
+  float *tmp = nullptr;
+  DQNB_CUDA(cudaMalloc(&tmp, sizeof(float) * g.flat));
+  DQNB_CUDA(cudaMemcpyAsync(tmp, in.data(), sizeof(float) * g.flat, cudaMemcpyHostToDevice, h->stream));
+  split_kernel<<<(unsigned)((g.flat + 255) / 256), 256, 0, h->stream>>>(tmp, h->P[net], h->P[net] + g.flat, g.flat);
+  DQNB_CUDA(cudaGetLastError());
+  DQNB_CUDA(cudaStreamSynchronize(h->stream));
+  DQNB_CUDA(cudaFree(tmp));
+  return 0;
+}
+
+static int read_flat(dqnb_handle h, const NetGeom &g, const float *dev_hi, const float *dev_lo, float *caffe_out) {
+  std::vector<float> a((size_t)g.flat), b;
+  DQNB_CUDA(cudaStreamSynchronize(h->stream));
+  DQNB_CUDA(cudaMemcpy(a.data(), dev_hi, sizeof(float) * g.flat, cudaMemcpyDeviceToHost));
+  if (dev_lo) {
+    b.resize((size_t)g.flat);
+    DQNB_CUDA(cudaMemcpy(b.data(), dev_lo, sizeof(float) * g.flat, cudaMemcpyDeviceToHost));
+    for (long long i = 0; i < g.flat; ++i) a[i] += b[i];
+  }
+  internal_to_caffe(g, a.data(), caffe_out);
+  return 0;
+}
+
+int dqnb_get_params(dqnb_handle h, int net, float *params) {
+  if (!h || net < 0 || net > 3 || !params) DQNB_FAIL("bad argument");
+  DQNB_CUDA(cudaSetDevice(h->cfg.device));
+  const NetGeom &g = (net & 1) ? h->gC : h->gA;
+  return read_flat(h, g, h->P[net], h->P[net] + g.flat, params);
+}
+
+int dqnb_clone_targets(dqnb_handle h) {
+  if (!h) DQNB_FAIL("null handle");
+  DQNB_CUDA(cudaSetDevice(h->cfg.device));
+  DQNB_CUDA(cudaMemcpyAsync(h->P[DQNB_ACTOR_TARGET], h->P[DQNB_ACTOR], sizeof(float) * 2 * h->gA.flat, cudaMemcpyDeviceToDevice, h->stream));
+  DQNB_CUDA(cudaMemcpyAsync(h->P[DQNB_CRITIC_TARGET], h->P[DQNB_CRITIC], sizeof(float) * 2 * h->gC.flat, cudaMemcpyDeviceToDevice, h->stream));
+  DQNB_CUDA(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int dqnb_init_params(dqnb_handle h, uint64_t seed, float stddev) {
+  if (!h) DQNB_FAIL("null handle");
+  std::mt19937 rng((uint32_t)seed);
+  std::normal_distribution<float> nd(0.f, stddev);
+  for (int net = 0; net < 2; ++net) {
+    const NetGeom &g = net ? h->gC : h->gA;
+    std::vector<float> p((size_t)g.caffe_count, 0.f);
+    for (int l = 0; l < g.n_hidden; ++l) {
+      const LayerGeom &L = g.L[l];
+      for (long long i = 0; i < (long long)L.n_real * L.k_real; ++i) p[L.cw_off + i] = nd(rng);
+    }
+    const int k_real = g.L[g.n_hidden - 1].n_real;
+    const int nh = g.critic ? 1 : 2;
+    const int rows[2] = {g.critic ? 1 : 4, 6};
+    for (int hd = 0; hd < nh; ++hd)
+      for (long long i = 0; i < (long long)rows[hd] * k_real; ++i) p[g.chw_off[hd] + i] = nd(rng);
+    if (dqnb_set_params(h, net, p.data())) return -1;
+  }
+  return dqnb_clone_targets(h);
+}
+
+static int upload_flat(dqnb_handle h, const NetGeom &g, const float *caffe, float *dev) {
+  std::vector<float> in;
+  caffe_to_internal(g, caffe, in);
+  DQNB_CUDA(cudaMemcpy(dev, in.data(), sizeof(float) * g.flat, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+static int pull_state(dqnb_handle h, StepState *s) {
+  DQNB_CUDA(cudaStreamSynchronize(h->stream));
+  DQNB_CUDA(cudaMemcpy(s, h->st, sizeof(StepState), cudaMemcpyDeviceToHost));
+  return 0;
+}
+static int push_state(dqnb_handle h, const StepState *s) {
+  DQNB_CUDA(cudaMemcpy(h->st, s, sizeof(StepState), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int dqnb_set_opt_state(dqnb_handle h, int net, const float *m, const float *v, int32_t iter) {
+  if (!h || net < 0 || net > 1) DQNB_FAIL("bad argument");
+  DQNB_CUDA(cudaSetDevice(h->cfg.device));
+  DQNB_CUDA(cudaStreamSynchronize(h->stream));
+  const NetGeom &g = net ? h->gC : h->gA;
+  if (m && upload_flat(h, g, m, h->Mo[net])) return -1;
+  if (v && upload_flat(h, g, v, h->Vo[net])) return -1;
+  StepState s;
+  if (pull_state(h, &s)) return -1;
+  if (net) s.critic_iter = iter; else s.actor_iter = iter;
+  return push_state(h, &s);
+}
+
+int dqnb_get_opt_state(dqnb_handle h, int net, float *m, float *v, int32_t *iter) {
+  if (!h || net < 0 || net > 1) DQNB_FAIL("bad argument");
+  DQNB_CUDA(cudaSetDevice(h->cfg.device));
+  const NetGeom &g = net ? h->gC : h->gA;
+  if (m && read_flat(h, g, h->Mo[net], nullptr, m)) return -1;
+  if (v && read_flat(h, g, h->Vo[net], nullptr, v)) return -1;
+  if (iter) {
+    StepState s;
+    if (pull_state(h, &s)) return -1;
+    *iter = net ? s.critic_iter : s.actor_iter;
+  }
+  return 0;
+}
+
+int dqnb_iters(dqnb_handle h, int32_t *actor_iter, int32_t *critic_iter) {
+  if (!h) DQNB_FAIL("null handle");
+  DQNB_CUDA(cudaSetDevice(h->cfg.device));
+  StepState s;
+  if (pull_state(h, &s)) return -1;
+  if (actor_iter) *actor_iter = s.actor_iter;
+  if (critic_iter) *critic_iter = s.critic_iter;
+  return 0;
+}
+
+// ----------------------------------- replay ring -----------------------------------------------
+static int push_ring_state(dqnb_handle h) {
+  // head/size live in StepState so the captured graph always sees the current ring
+  int hs[2] = {h->ring_head, h->ring_size};
+  DQNB_CUDA(cudaMemcpyAsync(&h->st->ring_head, hs, sizeof(hs), cudaMemcpyHostToDevice, h->stream));
+  return 0;
+}
+
+static int append_rows(dqnb_handle h, int32_t n, const float *s, const float *act10, const float *reward,
+                       const float *mc, const float *s_next, const uint8_t *terminal) {
+  const int cap = h->cfg.replay_capacity, S = h->S, Sp = h->Sp;
+  int done = 0;
+  while (done < n) {
+    const int chunk = std::min(n - done, h->stage_rows);
+    DQNB_CUDA(cudaStreamSynchronize(h->stream));   // staging buffers are reused
+    for (int i = 0; i < chunk; ++i) {
+      const int r = done + i;
+      float *ds = h->h_stage_s + (size_t)i * Sp, *dn = h->h_stage_sn + (size_t)i * Sp, *dm = h->h_stage_misc + (size_t)i * kMiscStride;
+      memcpy(ds, s + (size_t)r * S, sizeof(float) * S);
+      memset(ds + S, 0, sizeof(float) * (Sp - S));
+      const bool t = terminal[r] != 0;
+      if (!t && s_next) memcpy(dn, s_next + (size_t)r * S, sizeof(float) * S); else memset(dn, 0, sizeof(float) * S);
+      memset(dn + S, 0, sizeof(float) * (Sp - S));
+      memcpy(dm, act10 + (size_t)r * kActorOut, sizeof(float) * kActorOut);
+      dm[10] = reward[r]; dm[11] = mc[r]; dm[12] = t ? 1.f : 0.f; dm[13] = dm[14] = dm[15] = 0.f;
+    }
+    int tail = (h->ring_head + h->ring_size) % cap;
+    int left = chunk, src = 0;
+    while (left > 0) {
+      const int run = std::min(left, cap - tail);
+      DQNB_CUDA(cudaMemcpyAsync(h->ring_s + (size_t)tail * Sp, h->h_stage_s + (size_t)src * Sp, sizeof(float) * (size_t)run * Sp, cudaMemcpyHostToDevice, h->stream));
+      DQNB_CUDA(cudaMemcpyAsync(h->ring_sn + (size_t)tail * Sp, h->h_stage_sn + (size_t)src * Sp, sizeof(float) * (size_t)run * Sp, cudaMemcpyHostToDevice, h->stream));
+      DQNB_CUDA(cudaMemcpyAsync(h->ring_misc + (size_t)tail * kMiscStride, h->h_stage_misc + (size_t)src * kMiscStride, sizeof(float) * (size_t)run * kMiscStride, cudaMemcpyHostToDevice, h->stream));
+      tail = (tail + run) % cap; src += run; left -= run;
+    }
+    h->ring_size += chunk;
+    done += chunk;
+  }
+  return push_ring_state(h);
+}
+
+int dqnb_add_transitions(dqnb_handle h, int32_t n, const float *s, const float *act10, const float *reward,
+                         const float *mc_target, const float *s_next, const uint8_t *terminal) {
+  if (!h || n < 0 || (n > 0 && (!s || !act10 || !reward || !mc_target || !terminal))) DQNB_FAIL("bad argument");
+  if (n == 0) return 0;
+  DQNB_CUDA(cudaSetDevice(h->cfg.device));
+  const int cap = h->cfg.replay_capacity;
+  if (n >= cap) DQNB_FAIL("AddTransitions: %d rows do not fit capacity %d (dqn.cpp:776 keeps size < capacity)", n, cap);
+  // dqn.cpp:776-778: while (size + n >= capacity) pop_front()
+  while (h->ring_size + n >= cap && h->ring_size > 0) { h->ring_head = (h->ring_head + 1) % cap; h->ring_size--; }
+  return append_rows(h, n, s, act10, reward, mc_target, s_next, terminal);
+}
+
+int dqnb_add_transition(dqnb_handle h, const float *s, const float *act10, float reward, float mc_target,
+                        const float *s_next, uint8_t terminal) {
+  if (!h || !s || !act10) DQNB_FAIL("bad argument");
+  DQNB_CUDA(cudaSetDevice(h->cfg.device));
+  const int cap = h->cfg.replay_capacity;
+  // dqn.cpp:769-771: if (size == capacity) pop_front()
+  if (h->ring_size == cap) { h->ring_head = (h->ring_head + 1) % cap; h->ring_size--; }
+  return append_rows(h, 1, s, act10, &reward, &mc_target, s_next, &terminal);
+}
+
+int32_t dqnb_memory_size(dqnb_handle h) { return h ? h->ring_size : -1; }
+
+int dqnb_clear_memory(dqnb_handle h) {
+  if (!h) DQNB_FAIL("null handle");
+  DQNB_CUDA(cudaSetDevice(h->cfg.device));
+  h->ring_head = 0; h->ring_size = 0;
+  return push_ring_state(h);
+}
+
+int dqnb_get_transitions(dqnb_handle h, int32_t first, int32_t n, float *s, float *act10, float *reward,
+                         float *mc_target, float *s_next, uint8_t *terminal) {
+  if (!h || first < 0 || n < 0 || first + n > h->ring_size) DQNB_FAIL("bad range");
+  DQNB_CUDA(cudaSetDevice(h->cfg.device));
+  DQNB_CUDA(cudaStreamSynchronize(h->stream));
+  const int cap = h->cfg.replay_capacity, S = h->S, Sp = h->Sp;
+  std::vector<float> bs((size_t)Sp), bn((size_t)Sp), bm(kMiscStride);
+  // row-at-a-time is fine here: this is the snapshot path, not the hot path
+  std::vector<float> rs((size_t)n * Sp), rn((size_t)n * Sp), rm((size_t)n * kMiscStride);
+  int phys = (h->ring_head + first) % cap, left = n, dst = 0;
+  while (left > 0) {
+    const int run = std::min(left, cap - phys);
+    DQNB_CUDA(cudaMemcpy(rs.data() + (size_t)dst * Sp, h->ring_s + (size_t)phys * Sp, sizeof(float) * (size_t)run * Sp, cudaMemcpyDeviceToHost));
+    DQNB_CUDA(cudaMemcpy(rn.data() + (size_t)dst * Sp, h->ring_sn + (size_t)phys * Sp, sizeof(float) * (size_t)run * Sp, cudaMemcpyDeviceToHost));
+    DQNB_CUDA(cudaMemcpy(rm.data() + (size_t)dst * kMiscStride, h->ring_misc + (size_t)phys * kMiscStride, sizeof(float) * (size_t)run * kMiscStride, cudaMemcpyDeviceToHost));
+    phys = (phys + run) % cap; dst += run; left -= run;
+  }
+  for (int i = 0; i < n; ++i) {
+    if (s) memcpy(s + (size_t)i * S, rs.data() + (size_t)i * Sp, sizeof(float) * S);
+    if (s_next) memcpy(s_next + (size_t)i * S, rn.data() + (size_t)i * Sp, sizeof(float) * S);
+    const float *m = rm.data() + (size_t)i * kMiscStride;
+    if (act10) memcpy(act10 + (size_t)i * kActorOut, m, sizeof(float) * kActorOut);
+    if (reward) reward[i] = m[10];
+    if (mc_target) mc_target[i] = m[11];
+    if (terminal) terminal[i] = m[12] != 0.f;
+  }
+  return 0;
+}
+
+// ----------------------------------- update ----------------------------------------------------
+static int ensure_graph(dqnb_handle h, bool injected) {
+  cudaGraphExec_t *slot = injected ? &h->graph_injected : &h->graph_sampled;
+  if (*slot) return 0;
+  cudaGraph_t graph = nullptr;
+  int count = 0;
+  DQNB_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+  int rc = run_ops(h, h->update_ops, h->stream, injected, &count);
+  cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
+  if (rc) { if (graph) cudaGraphDestroy(graph); return -1; }
+  DQNB_CUDA(e);
+  DQNB_CUDA(cudaGraphInstantiate(slot, graph, 0));
+  DQNB_CUDA(cudaGraphDestroy(graph));
+  (injected ? h->kernels_per_update_injected : h->kernels_per_update_sampled) = count;
+  return 0;
+}
+
+static int enqueue_update(dqnb_handle h, bool injected) {
+  if (h->cfg.use_graph) {
+    if (ensure_graph(h, injected)) return -1;
+    DQNB_CUDA(cudaGraphLaunch(injected ? h->graph_injected : h->graph_sampled, h->stream));
+    h->launches += injected ? h->kernels_per_update_injected : h->kernels_per_update_sampled;
+  } else {
+    int count = 0;
+    if (run_ops(h, h->update_ops, h->stream, injected, &count)) return -1;
+    h->launches += count;
+  }
+  return 0;
+}
+
+static int reset_slots(dqnb_handle h) {
+  const int zero = 0;
+  DQNB_CUDA(cudaMemcpyAsync(&h->st->result_slot, &zero, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  return 0;
+}
+
+static int fetch_results(dqnb_handle h, int n, float *critic_loss, float *avg_q) {
+  DQNB_CUDA(cudaMemcpyAsync(h->h_results, h->results, sizeof(float) * 2 * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+  DQNB_CUDA(cudaStreamSynchronize(h->stream));
+  for (int i = 0; i < n; ++i) {
+    if (critic_loss) critic_loss[i] = h->h_results[2 * i];
+    if (avg_q) avg_q[i] = h->h_results[2 * i + 1];
+  }
+  return 0;
+}
+
+int dqnb_update(dqnb_handle h, int32_t n_updates, float *critic_loss, float *avg_q) {
+  if (!h || n_updates < 0) DQNB_FAIL("bad argument");
+  if (n_updates == 0) return 0;
+  if (h->ring_size <= 0) DQNB_FAIL("Update on an empty replay memory");
+  DQNB_CUDA(cudaSetDevice(h->cfg.device));
+  int done = 0;
+  while (done < n_updates) {
+    const int chunk = std::min(n_updates - done, h->max_slots);
+    if (reset_slots(h)) return -1;
+    for (int i = 0; i < chunk; ++i) if (enqueue_update(h, false)) return -1;
+    if (fetch_results(h, chunk, critic_loss ? critic_loss + done : nullptr, avg_q ? avg_q + done : nullptr)) return -1;
+    done += chunk;
+  }
+  return 0;
+}
+
+int dqnb_update_with_indices(dqnb_handle h, const int32_t *idx, float *critic_loss, float *avg_q) {
+  if (!h || !idx) DQNB_FAIL("bad argument");
+  DQNB_CUDA(cudaSetDevice(h->cfg.device));
+  for (int i = 0; i < h->B; ++i)
+    if (idx[i] < 0 || idx[i] >= h->ring_size) DQNB_FAIL("index %d out of range [0,%d)", idx[i], h->ring_size);
+  DQNB_CUDA(cudaMemcpyAsync(h->idx, idx, sizeof(int32_t) * h->B, cudaMemcpyHostToDevice, h->stream));
+  if (reset_slots(h)) return -1;
+  if (enqueue_update(h, true)) return -1;
+  return fetch_results(h, 1, critic_loss, avg_q);
+}
+
+int dqnb_benchmark(dqnb_handle h, int32_t n_updates, float *elapsed_ms) {
+  if (!h || n_updates <= 0 || !elapsed_ms) DQNB_FAIL("bad argument");
+  if (h->ring_size <= 0) DQNB_FAIL("Benchmark on an empty replay memory");
+  DQNB_CUDA(cudaSetDevice(h->cfg.device));
+  if (h->cfg.use_graph && ensure_graph(h, false)) return -1;
+  if (reset_slots(h)) return -1;
+  DQNB_CUDA(cudaStreamSynchronize(h->stream));
+  DQNB_CUDA(cudaEventRecord(h->ev0, h->stream));
+  for (int i = 0; i < n_updates; ++i) if (enqueue_update(h, false)) return -1;
+  DQNB_CUDA(cudaEventRecord(h->ev1, h->stream));
+  DQNB_CUDA(cudaEventSynchronize(h->ev1));
+  DQNB_CUDA(cudaEventElapsedTime(elapsed_ms, h->ev0, h->ev1));
+  return 0;
+}
+
+int dqnb_peek_sample_indices(dqnb_handle h, int32_t *idx) {
+  if (!h || !idx) DQNB_FAIL("bad argument");
+  DQNB_CUDA(cudaSetDevice(h->cfg.device));
+  sample_kernel<<<(h->B + 255) / 256, 256, 0, h->stream>>>(h->st, h->cfg.seed, h->B, h->idx);
+  DQNB_CUDA(cudaGetLastError());
+  DQNB_CUDA(cudaMemcpyAsync(idx, h->idx, sizeof(int32_t) * h->B, cudaMemcpyDeviceToHost, h->stream));
+  DQNB_CUDA(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+// ----------------------------------- act path --------------------------------------------------
+static int stage_rows_split(dqnb_handle h, int n, const float *src, int src_ld, int cols, const float *src2, int cols2,
+                            const SplitMat &X) {
+  // host-side split into (hi, lo) planes of the padded input block, one H2D per plane
+  const int ld = X.ld;
+  float *hi = h->h_act_in, *lo = h->h_act_in + (size_t)h->An * h->Kc;
+  memset(hi, 0, sizeof(float) * (size_t)n * ld);
+  memset(lo, 0, sizeof(float) * (size_t)n * ld);
+  for (int i = 0; i < n; ++i) {
+    for (int c = 0; c < cols; ++c) {
+      const float x = src[(size_t)i * src_ld + c], hh = tf32_hi(x);
+      hi[(size_t)i * ld + c] = hh; lo[(size_t)i * ld + c] = x - hh;
+    }
+    for (int c = 0; c < cols2; ++c) {
+      const float x = src2[(size_t)i * cols2 + c], hh = tf32_hi(x);
+      hi[(size_t)i * ld + cols + c] = hh; lo[(size_t)i * ld + cols + c] = x - hh;
+    }
+  }
+  DQNB_CUDA(cudaMemcpyAsync(X.p, hi, sizeof(float) * (size_t)n * ld, cudaMemcpyHostToDevice, h->stream));
+  DQNB_CUDA(cudaMemcpyAsync(X.p + X.plane(), lo, sizeof(float) * (size_t)n * ld, cudaMemcpyHostToDevice, h->stream));
+  return 0;
+}
+
+int dqnb_select_actions_async(dqnb_handle h, int32_t n, const float *states) {
+  if (!h || !states || n <= 0) DQNB_FAIL("bad argument");
+  if (n > h->cfg.max_act_batch) DQNB_FAIL("SelectActions: batch %d > max_act_batch %d (dqn.cpp:699)", n, h->cfg.max_act_batch);
+  DQNB_CUDA(cudaSetDevice(h->cfg.device));
+  DQNB_CUDA(cudaStreamSynchronize(h->stream));
+  if (stage_rows_split(h, n, states, h->S, h->S, nullptr, 0, h->Xact)) return -1;
+  int count = 0;
+  if (run_ops(h, h->act_ops, h->stream, false, &count)) return -1;
+  h->launches += count;
+  DQNB_CUDA(cudaMemcpyAsync(h->h_act_out, h->out16_act, sizeof(float) * (size_t)n * 16, cudaMemcpyDeviceToHost, h->stream));
+  return 0;
+}
+
+int dqnb_select_actions_wait(dqnb_handle h, int32_t n, float *out10) {
+  if (!h || !out10 || n <= 0) DQNB_FAIL("bad argument");
+  DQNB_CUDA(cudaStreamSynchronize(h->stream));
+  for (int i = 0; i < n; ++i) memcpy(out10 + (size_t)i * kActorOut, h->h_act_out + (size_t)i * 16, sizeof(float) * kActorOut);
+  return 0;
+}
+
+int dqnb_select_actions(dqnb_handle h, int32_t n, const float *states, float *out10) {
+  if (dqnb_select_actions_async(h, n, states)) return -1;
+  return dqnb_select_actions_wait(h, n, out10);
+}
+
+int dqnb_evaluate(dqnb_handle h, int32_t n, const float *states, const float *act10, float *q) {
+  if (!h || !states || !act10 || !q || n <= 0) DQNB_FAIL("bad argument");
+  if (n > h->cfg.max_act_batch) DQNB_FAIL("Evaluate: batch %d > max_act_batch %d", n, h->cfg.max_act_batch);
+  DQNB_CUDA(cudaSetDevice(h->cfg.device));
+  DQNB_CUDA(cudaStreamSynchronize(h->stream));
+  if (stage_rows_split(h, n, states, h->S, h->S, act10, kActorOut, h->Xeval)) return -1;
+  int count = 0;
+  if (run_ops(h, h->eval_ops, h->stream, false, &count)) return -1;
+  h->launches += count;
+  DQNB_CUDA(cudaMemcpyAsync(h->h_act_out, h->out16_act, sizeof(float) * (size_t)n * 16, cudaMemcpyDeviceToHost, h->stream));
+  DQNB_CUDA(cudaStreamSynchronize(h->stream));
+  for (int i = 0; i < n; ++i) q[i] = h->h_act_out[(size_t)i * 16];
+  return 0;
+}
+
+// ----------------------------------- multi-GPU -------------------------------------------------
+int dqnb_comm_unique_id(void *id128) {
+  if (!id128) DQNB_FAIL("null argument");
+  if (!nccl().lib || !nccl().GetUniqueId) DQNB_FAIL("libnccl.so.2 not loadable: %s", dlerror());
+  int r = nccl().GetUniqueId(id128);
+  if (r != 0) DQNB_FAIL("ncclGetUniqueId failed (%d)", r);
+  return 0;
+}
+
+int dqnb_comm_init(dqnb_handle h, const void *id128) {
+  if (!h || !id128) DQNB_FAIL("bad argument");
+  if (!nccl().lib || !nccl().CommInitRank) DQNB_FAIL("libnccl.so.2 not loadable");
+  DQNB_CUDA(cudaSetDevice(h->cfg.device));
+  Id128 id;
+  memcpy(&id, id128, sizeof(id));
+  int r = nccl().CommInitRank(&h->comm, h->cfg.world_size, id, h->cfg.rank);
+  if (r != 0) DQNB_FAIL("ncclCommInitRank failed: %s", nccl().GetErrorString ? nccl().GetErrorString(r) : "?");
+  return 0;
+}
+
+int dqnb_sync(dqnb_handle h) {
+  if (!h) DQNB_FAIL("null handle");
+  DQNB_CUDA(cudaSetDevice(h->cfg.device));
+  DQNB_CUDA(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int64_t dqnb_kernel_launches(dqnb_handle h) { return h ? h->launches : -1; }
+
+int64_t dqnb_debug_read(dqnb_handle h, const char *name, float *out, int64_t capacity) {
+  if (!h || !name || !out) return -1;
+  if (cudaSetDevice(h->cfg.device) != cudaSuccess) return -1;
+  cudaStreamSynchronize(h->stream);
+  const std::string n(name);
+  const float *src = nullptr;
+  int64_t cnt = 0;
+  if (n == "y") { src = h->y; cnt = h->B; }
+  else if (n == "q") { src = h->q; cnt = h->B; }
+  else if (n == "q_next") { src = h->q_next; cnt = h->B; }
+  else if (n == "q_pi") { src = h->q_pi; cnt = h->B; }
+  else if (n == "d_raw") { src = h->tap_raw; cnt = (int64_t)h->B * kActorOut; }
+  else if (n == "d_inv") { src = h->tap_inv; cnt = (int64_t)h->B * kActorOut; }
+  else if (n == "a_pi") {
+    cnt = (int64_t)h->B * kActorOut;
+    if (capacity < cnt) return -1;
+    std::vector<float> t((size_t)h->B * 16);
+    if (cudaMemcpy(t.data(), h->a16_pi, sizeof(float) * t.size(), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    for (int i = 0; i < h->B; ++i) memcpy(out + (size_t)i * kActorOut, t.data() + (size_t)i * 16, sizeof(float) * kActorOut);
+    return cnt;
+  } else if (n == "critic_grad" || n == "actor_grad") {
+    const int c = n == "critic_grad";
+    const NetGeom &g = c ? h->gC : h->gA;
+    cnt = g.caffe_count;
+    if (capacity < cnt) return -1;
+    if (read_flat(h, g, h->G[c], nullptr, out)) return -1;
+    return cnt;
+  } else if (n == "critic_gnorm" || n == "actor_gnorm") {
+    StepState s;
+    if (pull_state(h, &s)) return -1;
+    if (capacity < 1) return -1;
+    out[0] = s.gnorm[n == "critic_gnorm"];
+    return 1;
+  } else return -1;
+  if (capacity < cnt) return -1;
+  if (cudaMemcpy(out, src, sizeof(float) * cnt, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  return cnt;
+}
+
+// ----------------------------------- kernel unit test ------------------------------------------
+int dqnb_gemm_test(int device, int gemm_mode, int a_mn, int b_mn, int M, int N, int K, int splits,
+                   const float *A, const float *B, float *C, float *elapsed_ms) {
+  if (M % 64 || N % 64 || K % 32 || splits < 1 || splits > kGradSplits) DQNB_FAIL("gemm_test: M,N multiples of 64, K of 32, splits<=8");
+  DQNB_CUDA(cudaSetDevice(device));
+  DQNB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+  const size_t na = (size_t)M * K, nb = (size_t)N * K, nc = (size_t)M * N;
+  float *dA, *dB, *dAs, *dBs, *dP, *dC;
+  DQNB_CUDA(cudaMalloc(&dA, na * 4)); DQNB_CUDA(cudaMalloc(&dB, nb * 4));
+  DQNB_CUDA(cudaMalloc(&dAs, 2 * na * 4)); DQNB_CUDA(cudaMalloc(&dBs, 2 * nb * 4));
+  DQNB_CUDA(cudaMalloc(&dP, (size_t)splits * nc * 4)); DQNB_CUDA(cudaMalloc(&dC, nc * 4));
+  DQNB_CUDA(cudaMemcpy(dA, A, na * 4, cudaMemcpyHostToDevice));
+  DQNB_CUDA(cudaMemcpy(dB, B, nb * 4, cudaMemcpyHostToDevice));
+  split_kernel<<<(unsigned)((na + 255) / 256), 256>>>(dA, dAs, dAs + na, (long long)na);
+  split_kernel<<<(unsigned)((nb + 255) / 256), 256>>>(dB, dBs, dBs + nb, (long long)nb);
+  dqnb_config cfg;
+  dqnb_default_config(&cfg);
+  cfg.gemm_mode = gemm_mode;
+  Op op;
+  GemmParams &p = op.gemm.p;
+  memset(&p, 0, sizeof(p));
+  p.M = M; p.N = N; p.K = K; p.a_mn = a_mn; p.b_mn = b_mn; p.splits = splits; p.epi = EPI_PLAIN;
+  p.A = dAs; p.a_plane = (long long)na; p.lda = a_mn ? M : K;
+  p.B = dBs; p.b_plane = (long long)nb; p.ldb = b_mn ? N : K;
+  p.out = dP; p.out_split_stride = (long long)nc; p.ldo = N;
+  if (finish_gemm(cfg, &op)) return -1;
+  cudaEvent_t e0, e1;
+  DQNB_CUDA(cudaEventCreate(&e0)); DQNB_CUDA(cudaEventCreate(&e1));
+  const int reps = 5;
+  for (int r = 0; r < 1 + reps; ++r) {
+    if (r == 1) DQNB_CUDA(cudaEventRecord(e0, 0));
+    if (gemm_mode == DQNB_GEMM_TCGEN05_3XTF32) gemm_tc_kernel<<<op.grid, TC_THREADS, TC_SMEM_BYTES>>>(op.gemm);
+    else gemm_simt_kernel<<<op.grid, 256>>>(op.gemm.p);
+  }
+  DQNB_CUDA(cudaEventRecord(e1, 0));
+  DQNB_CUDA(cudaGetLastError());
+  DQNB_CUDA(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  DQNB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  if (elapsed_ms) *elapsed_ms = ms / reps;
+  sum_planes_kernel<<<(unsigned)((nc + 255) / 256), 256>>>(dP, (long long)nc, splits, dC, (long long)nc);
+  DQNB_CUDA(cudaGetLastError());
+  DQNB_CUDA(cudaMemcpy(C, dC, nc * 4, cudaMemcpyDeviceToHost));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(dA); cudaFree(dB); cudaFree(dAs); cudaFree(dBs); cudaFree(dP); cudaFree(dC);
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,371 @@
+// gemm.cuh — dense contraction kernels for the actor/critic towers (dqn.cpp:400-454) on sm_100a.
+//
+// Every GEMM operand lives in HBM as two fp32 planes [2][rows][ld] ("hi" = value rounded to TF32,
+// "lo" = exact remainder), see common.cuh.  One launch computes
+//      D[M x N] = sum_k A(m,k) * B(n,k)          (A, B given K-major or MN-major)
+// as hi*hi + hi*lo + lo*hi (3xTF32 ~ fp32 accuracy) and applies a fused epilogue:
+//   EPI_FWD   : InnerProduct forward + bias + leaky ReLU (Caffe InnerProduct/ReLU, dqn.cpp:340-356,
+//               :292-301) -> split planes of the next layer's input
+//   EPI_DX    : InnerProduct backward w.r.t. bottom + in-place leaky-ReLU backward of the layer
+//               below (mask from that layer's saved activation) -> split planes of dZ
+//   EPI_PLAIN : raw fp32 (weight-gradient partials of the split-K dW GEMMs, input diffs)
+//
+// gemm_tc_kernel   : TMA (cp.async.bulk.tensor.3d, 128B swizzle) -> 4-stage smem ring ->
+//                    tcgen05.mma.cta_group::1.kind::tf32 (M128 x N64 x K8, fp32 accumulators in
+//                    TMEM) -> tcgen05.ld epilogue.  Warp roles: 0 = TMA producer, 1 = MMA issuer
+//                    (+ TMEM alloc), 2..5 = epilogue (one TMEM lane quarter each).
+// gemm_simt_kernel : plain FFMA tiles over the same operands/epilogues (verification mode).
+#pragma once
+#include "common.cuh"
+
+namespace dqnb {
+
+enum { EPI_FWD = 0, EPI_DX = 1, EPI_PLAIN = 2 };
+
+struct GemmParams {
+  int M, N, K;            // padded problem: M rows of D, N cols of D, K contraction
+  int a_mn, b_mn;         // 0: K-major (contraction contiguous)  1: MN-major
+  int splits;             // split-K factor (gridDim.z)
+  int epi;
+  // raw operand views (SIMT mode and descriptors): plane 0 = hi, plane 1 = lo
+  const float *A; long long a_plane; int lda;
+  const float *B; long long b_plane; int ldb;
+  // outputs
+  float *out_hi; float *out_lo; int ldo;     // EPI_FWD / EPI_DX
+  float *out; long long out_split_stride;     // EPI_PLAIN: out + split*stride
+  const float *bias_hi; const float *bias_lo; // EPI_FWD (nullable)
+  const float *mask_hi; const float *mask_lo; int ldmask;  // EPI_DX
+  int apply_lrelu;                            // EPI_FWD: 0 for linear layers
+};
+
+struct alignas(64) GemmArgs {
+  CUtensorMap tmA;
+  CUtensorMap tmB;
+  GemmParams p;
+};
+
+// ---------------------------------------------------------------------------------------------
+// shared epilogue: CNT consecutive columns [n0, n0+CNT) of row m
+// ---------------------------------------------------------------------------------------------
+template <int CNT>
+__device__ __forceinline__ void epi_store(const GemmParams &p, int m, int n0, const float *acc,
+                                          int split) {
+  if (m >= p.M || n0 >= p.N) return;
+  if (p.epi == EPI_PLAIN) {
+    float *o = p.out + (long long)split * p.out_split_stride + (long long)m * p.ldo + n0;
+#pragma unroll
+    for (int j = 0; j < CNT; j += 4)
+      *reinterpret_cast<float4 *>(o + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+    return;
+  }
+  float hi[CNT], lo[CNT];
+  if (p.epi == EPI_FWD) {
+#pragma unroll
+    for (int j = 0; j < CNT; ++j) {
+      float v = acc[j];
+      if (p.bias_hi) v += p.bias_hi[n0 + j] + p.bias_lo[n0 + j];
+      if (p.apply_lrelu) v = fmaxf(v, 0.f) + kNegSlope * fminf(v, 0.f);
+      hi[j] = tf32_hi(v);
+      lo[j] = v - hi[j];
+    }
+  } else {  // EPI_DX
+    const float *mh = p.mask_hi + (long long)m * p.ldmask + n0;
+    const float *ml = p.mask_lo + (long long)m * p.ldmask + n0;
+#pragma unroll
+    for (int j = 0; j < CNT; j += 4) {
+      const float4 a = *reinterpret_cast<const float4 *>(mh + j);
+      const float4 b = *reinterpret_cast<const float4 *>(ml + j);
+      const float y[4] = {a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w};
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        // Caffe ReLU backward: diff * ((y > 0) + slope * (y <= 0)), y = in-place activation
+        const float v = acc[j + t] * (y[t] > 0.f ? 1.f : kNegSlope);
+        hi[j + t] = tf32_hi(v);
+        lo[j + t] = v - hi[j + t];
+      }
+    }
+  }
+  float *oh = p.out_hi + (long long)m * p.ldo + n0;
+  float *ol = p.out_lo + (long long)m * p.ldo + n0;
+#pragma unroll
+  for (int j = 0; j < CNT; j += 4) {
+    *reinterpret_cast<float4 *>(oh + j) = make_float4(hi[j], hi[j + 1], hi[j + 2], hi[j + 3]);
+    *reinterpret_cast<float4 *>(ol + j) = make_float4(lo[j], lo[j + 1], lo[j + 2], lo[j + 3]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// verification-mode kernel: 64x64 tile, 256 threads, 4x4 per thread, generic operand strides
+// ---------------------------------------------------------------------------------------------
+constexpr int ST = 64, SK = 16;
+
+__global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmParams p) {
+  __shared__ float As[SK][ST + 4];
+  __shared__ float Bs[SK][ST + 4];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.y * ST, n0 = blockIdx.x * ST, split = blockIdx.z;
+  const int kchunk = (p.K / SK + p.splits - 1) / p.splits * SK;
+  const int kb = split * kchunk, ke = min(p.K, kb + kchunk);
+  // element (r, k) of A lives at r*a_rs + k*a_cs
+  const long long a_rs = p.a_mn ? 1 : p.lda, a_cs = p.a_mn ? p.lda : 1;
+  const long long b_rs = p.b_mn ? 1 : p.ldb, b_cs = p.b_mn ? p.ldb : 1;
+  const int tx = tid % 16, ty = tid / 16;
+  float acc[4][4] = {};
+  for (int k0 = kb; k0 < ke; k0 += SK) {
+    for (int i = tid; i < ST * SK; i += 256) {
+      // thread -> (row, k) chosen so that the contiguous axis is the fast one
+      int r, k;
+      if (p.a_mn) { r = i % ST; k = i / ST; } else { k = i % SK; r = i / SK; }
+      float v = 0.f;
+      if (m0 + r < p.M && k0 + k < ke) {
+        const long long o = (long long)(m0 + r) * a_rs + (long long)(k0 + k) * a_cs;
+        v = p.A[o] + p.A[o + p.a_plane];
+      }
+      As[k][r] = v;
+      if (p.b_mn) { r = i % ST; k = i / ST; } else { k = i % SK; r = i / SK; }
+      v = 0.f;
+      if (n0 + r < p.N && k0 + k < ke) {
+        const long long o = (long long)(n0 + r) * b_rs + (long long)(k0 + k) * b_cs;
+        v = p.B[o] + p.B[o + p.b_plane];
+      }
+      Bs[k][r] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < SK; ++k) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = As[k][ty * 4 + i]; b[i] = Bs[k][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) epi_store<4>(p, m0 + ty * 4 + i, n0 + tx * 4, acc[i], split);
+}
+
+// ---------------------------------------------------------------------------------------------
+// tcgen05 / TMA / TMEM kernel
+// ---------------------------------------------------------------------------------------------
+constexpr int BM = 128, BN = 64, BK = 32, STAGES = 4;
+constexpr int A_PLANE_BYTES = BM * BK * 4;            // 16 KB: one plane of the A tile
+constexpr int B_PLANE_BYTES = BN * BK * 4;            //  8 KB
+constexpr int A_STAGE_BYTES = 2 * A_PLANE_BYTES;      // hi + lo
+constexpr int B_STAGE_BYTES = 2 * B_PLANE_BYTES;
+constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;   // 48 KB
+constexpr int MN_GROUP_BYTES = 2 * 32 * BK * 4;       // MN-major: one 32-wide group, hi then lo
+constexpr int TC_SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int TC_THREADS = 192;
+constexpr int TMEM_COLS = 64;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *tm, int c0, int c1,
+                                            int c2, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                            uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// UMMA shared-memory matrix descriptor (sm_100): start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46)
+// | version=1 [46,48) | layout_type [61,64) (2 = SWIZZLE_128B).
+//  K-major tile  : rows of 128 B (32 fp32 of K), 8-row swizzle atoms 1024 B apart (SBO); LBO unused.
+//  MN-major tile : 128 B rows hold 32 consecutive M/N elements for one k; 8 k-rows form an atom
+//                  (SBO = 1024 B to the next k-group); LBO = distance between 32-wide M/N groups.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) |
+         ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor: D=f32 [4,6)=1, A=tf32 [7,10)=2, B=tf32 [10,13)=2, a_major [15], b_major [16],
+// N>>3 [17,23), M>>4 [24,29)
+__device__ __forceinline__ uint32_t umma_idesc_tf32(int a_mn, int b_mn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+         ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmArgs args) {
+  extern __shared__ uint8_t smem_raw[];
+  const GemmParams &p = args.p;
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;          // SWIZZLE_128B atoms need 1024 B alignment
+  uint8_t *base_ptr = smem_raw + (base - raw);
+  const uint32_t bars = base + STAGES * STAGE_BYTES;     // full[STAGES], empty[STAGES], tmem_full
+  volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(base_ptr + STAGES * STAGE_BYTES + 128);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tile = blockIdx.x, m_tile = blockIdx.y, split = blockIdx.z;
+  const int kblocks = p.K / BK;
+  const int per = (kblocks + p.splits - 1) / p.splits;
+  const int kb0 = split * per;
+  const int kb1 = min(kblocks, kb0 + per);
+  const int iters = max(kb1 - kb0, 0);
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&args.tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&args.tmB) : "memory");
+    for (int i = 0; i < 2 * STAGES + 1; ++i) mbar_init(bars + 8 * i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32((const void *)tmem_slot)),
+                 "n"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer ----------------
+      for (int it = 0; it < iters; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+        const uint32_t full = bars + 8 * s, empty = bars + 8 * (STAGES + s);
+        mbar_wait(empty, ph ^ 1u);
+        mbar_expect_tx(full, STAGE_BYTES);
+        const uint32_t sa = base + s * STAGE_BYTES, sb = sa + A_STAGE_BYTES;
+        const int k0 = (kb0 + it) * BK;
+        if (!p.a_mn) {
+          tma_load_3d(sa, &args.tmA, k0, m_tile * BM, 0, full);              // box {32, 128, 2}
+        } else {
+#pragma unroll
+          for (int g = 0; g < BM / 32; ++g)                                   // box {32, 32, 2}
+            tma_load_3d(sa + g * MN_GROUP_BYTES, &args.tmA, m_tile * BM + g * 32, k0, 0, full);
+        }
+        if (!p.b_mn) {
+          tma_load_3d(sb, &args.tmB, k0, n_tile * BN, 0, full);              // box {32, 64, 2}
+        } else {
+#pragma unroll
+          for (int g = 0; g < BN / 32; ++g)
+            tma_load_3d(sb + g * MN_GROUP_BYTES, &args.tmB, n_tile * BN + g * 32, k0, 0, full);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---------------- MMA issuer (one thread) ----------------
+      const uint32_t idesc = umma_idesc_tf32(p.a_mn, p.b_mn);
+      for (int it = 0; it < iters; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+        const uint32_t full = bars + 8 * s, empty = bars + 8 * (STAGES + s);
+        mbar_wait(full, ph);
+        tc_fence_after();
+        const uint32_t sa = base + s * STAGE_BYTES, sb = sa + A_STAGE_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < BK / 8; ++ks) {
+          uint64_t a_hi, a_lo, b_hi, b_lo;
+          if (!p.a_mn) {
+            a_hi = umma_desc(sa + ks * 32, 16, 1024);
+            a_lo = umma_desc(sa + A_PLANE_BYTES + ks * 32, 16, 1024);
+          } else {
+            a_hi = umma_desc(sa + ks * 1024, MN_GROUP_BYTES, 1024);
+            a_lo = umma_desc(sa + 4096 + ks * 1024, MN_GROUP_BYTES, 1024);
+          }
+          if (!p.b_mn) {
+            b_hi = umma_desc(sb + ks * 32, 16, 1024);
+            b_lo = umma_desc(sb + B_PLANE_BYTES + ks * 32, 16, 1024);
+          } else {
+            b_hi = umma_desc(sb + ks * 1024, MN_GROUP_BYTES, 1024);
+            b_lo = umma_desc(sb + 4096 + ks * 1024, MN_GROUP_BYTES, 1024);
+          }
+          // small cross terms first, then the dominant hi*hi term
+          tc_mma_tf32(tmem, a_lo, b_hi, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+          tc_mma_tf32(tmem, a_hi, b_lo, idesc, 1u);
+          tc_mma_tf32(tmem, a_hi, b_hi, idesc, 1u);
+        }
+        tc_commit(empty);                  // frees the smem stage when these MMAs retire
+      }
+      tc_commit(bars + 8 * (2 * STAGES));  // accumulator complete -> epilogue
+    }
+  } else {
+    // ---------------- epilogue: TMEM -> registers -> HBM ----------------
+    const uint32_t tfull = bars + 8 * (2 * STAGES);
+    const int q = warp & 3;                // TMEM lane quarter this warp may read
+    const int row = m_tile * BM + q * 32 + lane;
+    float v[32];
+    if (iters > 0) {
+      mbar_wait(tfull, 0);
+      tc_fence_after();
+    }
+#pragma unroll
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      if (iters > 0) {
+        uint32_t r[32];
+        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+              "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+              "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
+              "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]),
+              "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+      }
+      epi_store<32>(p, row, n_tile * BN + c0, v, split);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS)
+                 : "memory");
+  }
+}
+
+}  // namespace dqnb

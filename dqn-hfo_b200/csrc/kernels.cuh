@@ -1,0 +1,498 @@
+// kernels.cuh — the non-GEMM kernels of one UpdateActorCritic (dqn.cpp:828-972): index sampling,
+// replay gather, linear heads, TD target / Euclidean loss, inverting gradients, bias gradients,
+// gradient reduction + global-norm clip, Adam + soft target update.  All HBM/L2-bound; loads are
+// coalesced along the contiguous (feature) axis and vectorised where the layout allows.
+#pragma once
+#include "common.cuh"
+
+namespace dqnb {
+
+constexpr int kGradSplits = 8;      // planes of the gradient-partial buffer
+constexpr int kMaxSegs = 2 * 8 + 4; // parameter blobs per net
+
+// Device-resident scalars so that one captured graph serves every update.
+struct StepState {
+  int actor_iter, critic_iter;      // Solver::iter() of each net (dqn.hpp:129-130)
+  unsigned long long step;          // update counter: keys the index sampler
+  int ring_head, ring_size;         // replay ring: physical index of the oldest row, fill
+  float step_critic, step_actor;    // lr * Adam bias correction for this update
+  int do_soft;                      // dqn.cpp:967
+  int result_slot;                  // where finalize writes (critic_loss, avg_q)
+  float gnorm[2];                   // [actor, critic] L2 norm seen by ClipGradients
+};
+
+struct HyperParams {
+  double gamma, beta;
+  float tau;
+  int soft_update_freq;
+  float actor_lr, critic_lr, beta1, beta2, eps, clip;
+  float inv_batch_global;           // 1 / (batch * world_size): EuclideanLoss 1/N
+};
+
+// -------------------------------------------------------------------------------------------
+__global__ void prep_kernel(StepState *st, HyperParams hp) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  // AdamSolver::ComputeUpdateValue: t = iter + 1; correction evaluated in double (std::pow(float,int))
+  const int tc = st->critic_iter + 1, ta = st->actor_iter + 1;
+  const double b1 = (double)hp.beta1, b2 = (double)hp.beta2;
+  const float cc = (float)(sqrt(1.0 - pow(b2, (double)tc)) / (1.0 - pow(b1, (double)tc)));
+  const float ca = (float)(sqrt(1.0 - pow(b2, (double)ta)) / (1.0 - pow(b1, (double)ta)));
+  st->step_critic = __fmul_rn(hp.critic_lr, cc);
+  st->step_actor = __fmul_rn(hp.actor_lr, ca);
+  const int mx = max(ta, tc);       // max_iter() after both solvers stepped (dqn.cpp:967)
+  st->do_soft = (hp.soft_update_freq > 0 && mx % hp.soft_update_freq == 0) ? 1 : 0;
+}
+
+__global__ void finalize_kernel(StepState *st, const float *g_critic_tail, const float *g_actor_tail,
+                                float *results, int max_slots) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const int slot = st->result_slot;
+  if (slot < max_slots) {
+    results[2 * slot + 0] = g_critic_tail[0];   // critic_loss (dqn.cpp:905)
+    results[2 * slot + 1] = g_actor_tail[0];    // avg_q       (dqn.cpp:915)
+  }
+  st->result_slot = slot + 1;
+  st->critic_iter += 1;                         // Solver::Step ++iter_ (dqn.cpp:904)
+  st->actor_iter += 1;                          // set_iter(iter+1)     (dqn.cpp:965)
+  st->step += 1;
+}
+
+// SampleTransitionsFromMemory (dqn.cpp:501-509): B uniform draws with replacement in [0,size)
+__global__ void sample_kernel(const StepState *st, unsigned long long seed, int B, int32_t *idx) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= B) return;
+  const int size = st->ring_size;
+  idx[n] = size > 0 ? sample_index(seed, st->step, (uint32_t)n, (uint32_t)size) : 0;
+}
+
+// -------------------------------------------------------------------------------------------
+// Replay gather (dqn.cpp:859-887): one block per minibatch row, threads along the feature axis.
+struct GatherArgs {
+  const StepState *st;
+  const int32_t *idx;
+  const float *ring_s, *ring_sn, *ring_misc;
+  int cap, B, Bp, S, Sp, Kc;
+  float *Xs, *Xsn;           // [2][Bp][Sp]   actor inputs: s, s'
+  float *Xc, *Xct, *Xcp;     // [2][Bp][Kc]   critic inputs: (s,a,p), (s',.), (s,.)
+  float *reward, *mc, *term; // [Bp]
+};
+
+__global__ void __launch_bounds__(128) gather_kernel(const GatherArgs a) {
+  const int n = blockIdx.x;
+  const bool valid = n < a.B;
+  long long phys = 0;
+  float misc_term = 1.f;
+  if (valid) {
+    phys = ((long long)a.st->ring_head + a.idx[n]) % a.cap;
+    misc_term = a.ring_misc[phys * kMiscStride + 12];
+  }
+  const bool has_next = valid && misc_term == 0.f;
+  const long long pS = (long long)a.Bp * a.Sp, pK = (long long)a.Bp * a.Kc;
+  for (int c = threadIdx.x; c < a.Kc; c += blockDim.x) {
+    float sv = 0.f, snv = 0.f;
+    if (c < a.Sp) {
+      if (valid) sv = a.ring_s[phys * a.Sp + c];
+      if (has_next) snv = a.ring_sn[phys * a.Sp + c];
+      const long long o = (long long)n * a.Sp + c;
+      float h = tf32_hi(sv);
+      a.Xs[o] = h; a.Xs[o + pS] = sv - h;
+      h = tf32_hi(snv);
+      a.Xsn[o] = h; a.Xsn[o + pS] = snv - h;
+    }
+    float xc = 0.f;
+    if (c < a.S) xc = sv;
+    else if (c < a.S + kActorOut && valid) xc = a.ring_misc[phys * kMiscStride + (c - a.S)];
+    const long long o = (long long)n * a.Kc + c;
+    float h = tf32_hi(xc);
+    a.Xc[o] = h; a.Xc[o + pK] = xc - h;
+    const float xt = c < a.S ? snv : 0.f;   // (s', a') : a' filled by the target-actor head
+    h = tf32_hi(xt);
+    a.Xct[o] = h; a.Xct[o + pK] = xt - h;
+    const float xp = c < a.S ? sv : 0.f;    // (s, a_pi): a_pi filled by the actor head
+    h = tf32_hi(xp);
+    a.Xcp[o] = h; a.Xcp[o + pK] = xp - h;
+  }
+  if (threadIdx.x == 0) {
+    a.reward[n] = valid ? a.ring_misc[phys * kMiscStride + 10] : 0.f;
+    a.mc[n] = valid ? a.ring_misc[phys * kMiscStride + 11] : 0.f;
+    a.term[n] = misc_term;
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Linear heads (dqn.cpp:426-427, :450): out[n][j] = h[n] . W[j] + b[j], one warp per row.
+struct HeadArgs {
+  const float *H; long long h_plane; int ldh; int Kp;   // top tower activation [2][rows][ldh]
+  const float *W; long long w_plane;                    // head weights [2][..] rows of Kp
+  const float *bias; long long b_plane;
+  int J;                       // rows of W in use (10 actor, 1 critic)
+  int rows;                    // valid rows (B, or n for the act path)
+  float *out16;                // [rows_pad][16] fp32 (nullable)
+  float *dst; long long dst_plane; int ldd; int dst_col;  // also scatter split(out) into a critic input
+};
+
+__global__ void __launch_bounds__(256) head_fwd_kernel(const HeadArgs a) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.x * 8 + warp;
+  if (n >= a.rows) return;
+  const float *hh = a.H + (long long)n * a.ldh;
+  float acc[kActorOut];
+#pragma unroll
+  for (int j = 0; j < kActorOut; ++j) acc[j] = 0.f;
+  for (int k = lane; k < a.Kp; k += 32) {
+    const float x = hh[k] + hh[k + a.h_plane];
+#pragma unroll
+    for (int j = 0; j < kActorOut; ++j)
+      if (j < a.J) {
+        const long long o = (long long)j * a.Kp + k;
+        acc[j] = fmaf(x, a.W[o] + a.W[o + a.w_plane], acc[j]);
+      }
+  }
+#pragma unroll
+  for (int j = 0; j < kActorOut; ++j)
+    if (j < a.J) acc[j] = warp_sum(acc[j]);
+  if (lane < a.J) {
+    float v = 0.f;
+#pragma unroll
+    for (int j = 0; j < kActorOut; ++j)
+      if (j == lane) v = acc[j];
+    v += a.bias[lane] + a.bias[lane + a.b_plane];
+    if (a.out16) a.out16[(long long)n * 16 + lane] = v;
+    if (a.dst) {
+      const long long o = (long long)n * a.ldd + a.dst_col + lane;
+      const float h = tf32_hi(v);
+      a.dst[o] = h; a.dst[o + a.dst_plane] = v - h;
+    }
+  }
+}
+
+// TD target (dqn.cpp:892-900), Euclidean loss forward/backward, policy-pass seed (dqn.cpp:918-921)
+enum { QMODE_TARGET = 0, QMODE_LOSS = 1, QMODE_POLICY = 2 };
+struct QArgs {
+  int mode, B;
+  const float *q16;            // critic head output [rows][16], column 0
+  const float *reward, *mc, *term;
+  float *y;                    // TARGET: out ; LOSS: in
+  float *q_tap;                // TARGET: q_next ; LOSS: q ; POLICY: q_pi
+  float *d16;                  // LOSS: dq = (q-y)/N ; POLICY: -1
+  double *part;                // per-block partial: LOSS sum (q-y)^2 ; POLICY sum q
+  HyperParams hp;
+};
+
+__global__ void __launch_bounds__(256) q_kernel(const QArgs a) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  double contrib = 0.0;
+  if (n < a.B) {
+    const float q = a.q16[(long long)n * 16];
+    if (a.mode == QMODE_TARGET) {
+      const bool terminal = a.term[n] != 0.f;
+      // float off = terminal ? r : r + gamma_*q' (double expr narrowed); float target = beta*on + (1-beta)*off
+      const float off = terminal ? a.reward[n] : (float)((double)a.reward[n] + a.hp.gamma * (double)q);
+      a.y[n] = (float)(a.hp.beta * (double)a.mc[n] + (1 - a.hp.beta) * (double)off);
+      a.q_tap[n] = terminal ? 0.f : q;
+    } else if (a.mode == QMODE_LOSS) {
+      const float diff = q - a.y[n];
+      a.d16[(long long)n * 16] = __fmul_rn(a.hp.inv_batch_global, diff);
+      a.q_tap[n] = q;
+      contrib = (double)diff * (double)diff;
+    } else {
+      a.d16[(long long)n * 16] = -1.0f;
+      a.q_tap[n] = q;
+      contrib = (double)q;
+    }
+  }
+  if (a.mode == QMODE_TARGET) return;
+  __shared__ double red[8];
+  contrib = warp_sum_d(contrib);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = contrib;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
+    a.part[blockIdx.x] = s;
+  }
+}
+
+// Head backward w.r.t. the tower top + leaky mask of that layer:
+//   dZ[n][k] = (sum_j d16[n][j] * W[j][k]) * relu'(h[n][k])       (Split sums the two actor heads)
+struct HeadBwdXArgs {
+  const float *d16; int J;
+  const float *W; long long w_plane; int Kp;
+  const float *H; long long h_plane; int ldh;
+  float *dZ; long long dz_plane; int rows_pad;
+};
+__global__ void __launch_bounds__(256) head_bwd_x_kernel(const HeadBwdXArgs a) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)a.rows_pad * a.Kp) return;
+  const int n = (int)(i / a.Kp), k = (int)(i % a.Kp);
+  float acc = 0.f;
+  for (int j = 0; j < a.J; ++j) {
+    const long long o = (long long)j * a.Kp + k;
+    acc = fmaf(a.d16[(long long)n * 16 + j], a.W[o] + a.W[o + a.w_plane], acc);
+  }
+  const long long ho = (long long)n * a.ldh + k;
+  const float y = a.H[ho] + a.H[ho + a.h_plane];
+  const float v = acc * (y > 0.f ? 1.f : kNegSlope);
+  const float h = tf32_hi(v);
+  a.dZ[ho] = h; a.dZ[ho + a.dz_plane] = v - h;
+}
+
+// Head weight/bias gradients: dW[j][k] = sum_n d16[n][j] h[n][k] ; db[j] = sum_n d16[n][j].
+// grid (Kp/128, kGradSplits); 512 threads = 4 row sub-groups x 128 columns.
+struct HeadBwdWArgs {
+  const float *d16; int J;
+  const float *H; long long h_plane; int ldh; int Kp;
+  int rows_pad;
+  float *gpart; long long gpart_stride; long long hw_off, hb_off;
+};
+__global__ void __launch_bounds__(512) head_bwd_w_kernel(const HeadBwdWArgs a) {
+  __shared__ float red[4][kActorOut][128];
+  const int k = blockIdx.x * 128 + (threadIdx.x & 127), sub = threadIdx.x >> 7, split = blockIdx.y;
+  const int per = a.rows_pad / kGradSplits;
+  const int r0 = split * per, r1 = r0 + per;
+  float acc[kActorOut];
+#pragma unroll
+  for (int j = 0; j < kActorOut; ++j) acc[j] = 0.f;
+  if (k < a.Kp)
+    for (int n = r0 + sub; n < r1; n += 4) {
+      const long long ho = (long long)n * a.ldh + k;
+      const float x = a.H[ho] + a.H[ho + a.h_plane];
+#pragma unroll
+      for (int j = 0; j < kActorOut; ++j)
+        if (j < a.J) acc[j] = fmaf(a.d16[(long long)n * 16 + j], x, acc[j]);
+    }
+#pragma unroll
+  for (int j = 0; j < kActorOut; ++j) red[sub][j][threadIdx.x & 127] = acc[j];
+  __syncthreads();
+  float *g = a.gpart + (long long)split * a.gpart_stride;
+  if (sub == 0 && k < a.Kp)
+    for (int j = 0; j < a.J; ++j)
+      g[a.hw_off + (long long)j * a.Kp + k] =
+          (red[0][j][threadIdx.x] + red[1][j][threadIdx.x]) + (red[2][j][threadIdx.x] + red[3][j][threadIdx.x]);
+  if (blockIdx.x == 0 && sub == 1 && (threadIdx.x & 127) < a.J) {
+    const int j = threadIdx.x & 127;
+    float s = 0.f;
+    for (int n = r0; n < r1; ++n) s += a.d16[(long long)n * 16 + j];
+    g[a.hb_off + j] = s;
+  }
+}
+
+// Bias gradients of the tower layers: db_l[c] = sum_n dZ_l[n][c] (Caffe: gemv(dY^T, ones)).
+struct ColsumArgs {
+  int n_layers, rows_pad;
+  const float *dZ[8]; long long plane[8]; int ld[8]; int Np[8]; long long b_off[8];
+  int blk_begin[9];            // prefix sums of Np/128 column blocks
+  float *gpart; long long gpart_stride;
+};
+__global__ void __launch_bounds__(512) colsum_kernel(const ColsumArgs a) {
+  __shared__ float red[4][128];
+  int l = 0;
+  while (l + 1 < a.n_layers && (int)blockIdx.x >= a.blk_begin[l + 1]) ++l;
+  const int c = ((int)blockIdx.x - a.blk_begin[l]) * 128 + (threadIdx.x & 127);
+  const int sub = threadIdx.x >> 7, split = blockIdx.y;
+  const int per = a.rows_pad / kGradSplits;
+  const int r0 = split * per, r1 = r0 + per;
+  float acc = 0.f;
+  if (c < a.Np[l])
+    for (int n = r0 + sub; n < r1; n += 4) {
+      const long long o = (long long)n * a.ld[l] + c;
+      acc += a.dZ[l][o] + a.dZ[l][o + a.plane[l]];
+    }
+  red[sub][threadIdx.x & 127] = acc;
+  __syncthreads();
+  if (sub == 0 && c < a.Np[l])
+    a.gpart[(long long)split * a.gpart_stride + a.b_off[l] + c] =
+        (red[0][threadIdx.x] + red[1][threadIdx.x]) + (red[2][threadIdx.x] + red[3][threadIdx.x]);
+}
+
+// Inverting gradients (dqn.cpp:927-957) on the critic's input diff columns [S, S+10).
+struct InvertArgs {
+  int B, Bp, S, ldin;
+  const float *d_in;           // [Bp][ldin] fp32: dL/d(critic input)
+  const float *a16;            // actor outputs [Bp][16]
+  float *d16;                  // out: top diffs of the actor heads [Bp][16]
+  float *tap_raw, *tap_inv;    // [Bp][10] debug taps
+};
+__global__ void __launch_bounds__(256) invert_kernel(const InvertArgs a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.Bp * 16) return;
+  const int n = i >> 4, h = i & 15;
+  float diff = 0.f;
+  if (n < a.B && h < kActorOut) {
+    diff = a.d_in[(long long)n * a.ldin + a.S + h];
+    a.tap_raw[n * kActorOut + h] = diff;
+    const float output = a.a16[i];
+    float mn, mx;
+    if (h < kActionSize) { mn = -1.0f; mx = 1.0f; }
+    else if (h == kActionSize + 0 || h == kActionSize + 4) { mn = 0.f; mx = 100.f; }
+    else { mn = -180.f; mx = 180.f; }
+    if (diff < 0) diff *= (mx - output) / (mx - mn);
+    else if (diff > 0) diff *= (output - mn) / (mx - mn);
+    a.tap_inv[n * kActorOut + h] = diff;
+  }
+  a.d16[i] = diff;
+}
+
+// -------------------------------------------------------------------------------------------
+// Gradient reduction over split planes + sum of squares (SGDSolver::ClipGradients numerator).
+struct SegTable {
+  int n;
+  long long begin[kMaxSegs], end[kMaxSegs];
+  int nsplit[kMaxSegs];
+};
+struct ReduceArgs {
+  SegTable segs;
+  long long flat;
+  const float *gpart; long long gpart_stride;
+  float *G;                    // [flat + 4]; tail[0] carries the scalar of this pass
+  float *norm_part;            // per-block sum of squares
+  const double *scal_part; int n_scal; float scal_scale;   // tail[0] = scale * sum(scal_part)
+  int do_reduce, do_sumsq;
+};
+__global__ void __launch_bounds__(256) reduce_kernel(const ReduceArgs a) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  float ss = 0.f;
+  if (i < a.flat) {
+    float4 g;
+    if (a.do_reduce) {
+      int s = 0;
+      while (s + 1 < a.segs.n && i >= a.segs.end[s]) ++s;
+      const int ns = a.segs.nsplit[s];
+      g = *reinterpret_cast<const float4 *>(a.gpart + i);
+      for (int p = 1; p < ns; ++p) {
+        const float4 t = *reinterpret_cast<const float4 *>(a.gpart + (long long)p * a.gpart_stride + i);
+        g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
+      }
+      *reinterpret_cast<float4 *>(a.G + i) = g;
+    } else {
+      g = *reinterpret_cast<const float4 *>(a.G + i);
+    }
+    ss = g.x * g.x + g.y * g.y + g.z * g.z + g.w * g.w;
+  }
+  if (a.do_sumsq) {
+    __shared__ float red[8];
+    ss = warp_sum(ss);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float s = 0.f;
+      for (int w = 0; w < 8; ++w) s += red[w];
+      a.norm_part[blockIdx.x] = s;
+    }
+  }
+  if (a.do_reduce && blockIdx.x == 0 && threadIdx.x == 0) {
+    double s = 0.0;
+    for (int j = 0; j < a.n_scal; ++j) s += a.scal_part[j];
+    a.G[a.flat] = (float)(s * (double)a.scal_scale);
+  }
+}
+
+// ClipGradients scale + AdamSolver::ComputeUpdateValue + Net::Update (+ SoftUpdateNet dqn.cpp:1085-1096)
+struct AdamArgs {
+  long long flat;
+  const float *G;
+  const float *norm_part; int n_norm;
+  float *M, *V;
+  float *P; long long p_plane;      // online params [2][flat]
+  float *T; long long t_plane;      // target params [2][flat]
+  const StepState *st; StepState *st_out;
+  int is_critic;
+  HyperParams hp;
+};
+__global__ void __launch_bounds__(256) adam_kernel(const AdamArgs a) {
+  __shared__ float s_scale;
+  __shared__ double red[8];
+  {
+    double s = 0.0;
+    for (int j = threadIdx.x; j < a.n_norm; j += blockDim.x) s += (double)a.norm_part[j];
+    s = warp_sum_d(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int w = 0; w < 8; ++w) t += red[w];
+      const float l2 = sqrtf((float)t);
+      s_scale = (a.hp.clip >= 0.f && l2 > a.hp.clip) ? a.hp.clip / l2 : 1.0f;
+      if (blockIdx.x == 0) a.st_out->gnorm[a.is_critic] = l2;
+    }
+    __syncthreads();
+  }
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i >= a.flat) return;
+  const float scale = s_scale;
+  const float step = a.is_critic ? a.st->step_critic : a.st->step_actor;
+  const int do_soft = a.st->do_soft;
+  const float b1 = a.hp.beta1, b2 = a.hp.beta2, a1 = 1.f - a.hp.beta1, a2 = 1.f - a.hp.beta2;
+  const float keep = 1 - a.hp.tau;
+  const float4 g4 = *reinterpret_cast<const float4 *>(a.G + i);
+  float4 m4 = *reinterpret_cast<const float4 *>(a.M + i);
+  float4 v4 = *reinterpret_cast<const float4 *>(a.V + i);
+  const float4 ph = *reinterpret_cast<const float4 *>(a.P + i);
+  const float4 pl = *reinterpret_cast<const float4 *>(a.P + a.p_plane + i);
+  float g[4] = {g4.x, g4.y, g4.z, g4.w}, m[4] = {m4.x, m4.y, m4.z, m4.w}, v[4] = {v4.x, v4.y, v4.z, v4.w};
+  float w[4] = {ph.x + pl.x, ph.y + pl.y, ph.z + pl.z, ph.w + pl.w};
+  float wh[4], wl[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const float gi = scale != 1.0f ? __fmul_rn(g[t], scale) : g[t];   // Blob::scale_diff
+    m[t] = __fadd_rn(__fmul_rn(m[t], b1), __fmul_rn(a1, gi));         // axpby = sscal + saxpy
+    v[t] = __fadd_rn(__fmul_rn(v[t], b2), __fmul_rn(a2, __fmul_rn(gi, gi)));
+    const float den = __fadd_rn(sqrtf(v[t]), a.hp.eps);
+    const float d = __fmul_rn(step, m[t] / den);
+    w[t] = __fsub_rn(w[t], d);                                         // Blob::Update
+    wh[t] = tf32_hi(w[t]);
+    wl[t] = w[t] - wh[t];
+  }
+  *reinterpret_cast<float4 *>(a.M + i) = make_float4(m[0], m[1], m[2], m[3]);
+  *reinterpret_cast<float4 *>(a.V + i) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4 *>(a.P + i) = make_float4(wh[0], wh[1], wh[2], wh[3]);
+  *reinterpret_cast<float4 *>(a.P + a.p_plane + i) = make_float4(wl[0], wl[1], wl[2], wl[3]);
+  if (do_soft) {
+    const float4 th = *reinterpret_cast<const float4 *>(a.T + i);
+    const float4 tl = *reinterpret_cast<const float4 *>(a.T + a.t_plane + i);
+    float tt[4] = {th.x + tl.x, th.y + tl.y, th.z + tl.z, th.w + tl.w};
+    float oh[4], ol[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      // caffe_cpu_axpby(N, tau, from, 1-tau, to): to *= (1-tau); to += tau*from
+      const float x = __fadd_rn(__fmul_rn(tt[t], keep), __fmul_rn(a.hp.tau, w[t]));
+      oh[t] = tf32_hi(x);
+      ol[t] = x - oh[t];
+    }
+    *reinterpret_cast<float4 *>(a.T + i) = make_float4(oh[0], oh[1], oh[2], oh[3]);
+    *reinterpret_cast<float4 *>(a.T + a.t_plane + i) = make_float4(ol[0], ol[1], ol[2], ol[3]);
+  }
+}
+
+// split an fp32 array into (hi, lo) planes / join it back (parameter import / export)
+__global__ void split_kernel(const float *x, float *hi, float *lo, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float h = tf32_hi(x[i]);
+  hi[i] = h; lo[i] = x[i] - h;
+}
+__global__ void join_kernel(const float *hi, const float *lo, float *x, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) x[i] = hi[i] + lo[i];
+}
+// standalone gemm test: sum split planes
+__global__ void sum_planes_kernel(const float *part, long long stride, int planes, float *out, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.f;
+  for (int p = 0; p < planes; ++p) s += part[(long long)p * stride + i];
+  out[i] = s;
+}
+
+}  // namespace dqnb

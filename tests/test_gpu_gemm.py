@@ -1,0 +1,52 @@
+"""Kernel unit tests: the dense contraction kernels (csrc/gemm.cuh) against float64 numpy, for every
+operand-major combination the layers use (forward: K/K, dX: K/MN, dW: MN/MN) and split-K."""
+import numpy as np
+import pytest
+
+from util import pkg, relerr
+
+pytestmark = pytest.mark.gpu
+
+CASES = [  # (a_mn, b_mn, M, N, K, splits)
+    (0, 0, 128, 64, 32, 1),
+    (0, 0, 256, 128, 96, 1),
+    (0, 0, 1024, 512, 1024, 1),     # layer-2 forward at batch 1024
+    (0, 1, 128, 64, 64, 1),
+    (0, 1, 1024, 1024, 512, 1),     # layer-2 dX
+    (1, 1, 128, 64, 128, 1),
+    (1, 1, 512, 1024, 1024, 2),     # layer-2 dW, split-K over the minibatch
+    (1, 1, 64, 128, 256, 4),        # M smaller than the 128-row tile (TMA zero fill)
+    (1, 0, 128, 64, 64, 1),
+    (0, 0, 128, 64, 4096, 8),
+]
+
+
+@pytest.mark.parametrize("mode", [1, 0], ids=["simt_fp32", "tcgen05_3xtf32"])
+@pytest.mark.parametrize("a_mn,b_mn,M,N,K,splits", CASES)
+def test_gemm_matches_float64(mode, a_mn, b_mn, M, N, K, splits):
+    P = pkg()
+    rng = np.random.default_rng(M + N + K + a_mn * 2 + b_mn)
+    A = rng.normal(0, 1, (M, K)).astype(np.float32)
+    B = rng.normal(0, 1, (N, K)).astype(np.float32)
+    ref = A.astype(np.float64) @ B.astype(np.float64).T
+    Ain = np.ascontiguousarray(A.T) if a_mn else A
+    Bin = np.ascontiguousarray(B.T) if b_mn else B
+    Cm, ms = P.gemm_test(mode, a_mn, b_mn, M, N, K, splits, Ain, Bin)
+    # 3xTF32 drops only lo*lo terms (~2^-22 per product): fp32-class accuracy
+    assert relerr(Cm, ref) < 2e-6, (relerr(Cm, ref), ms)
+
+
+def test_gemm_exact_on_small_integers():
+    """Integer-valued operands are exact in TF32, so any layout/descriptor bug shows up as a
+    bit-level mismatch rather than a tolerance question."""
+    P = pkg()
+    rng = np.random.default_rng(3)
+    for a_mn, b_mn in ((0, 0), (0, 1), (1, 1), (1, 0)):
+        M, N, K = 256, 128, 64
+        A = rng.integers(-4, 5, (M, K)).astype(np.float32)
+        B = rng.integers(-4, 5, (N, K)).astype(np.float32)
+        ref = (A.astype(np.int64) @ B.astype(np.int64).T).astype(np.float32)
+        Ain = np.ascontiguousarray(A.T) if a_mn else A
+        Bin = np.ascontiguousarray(B.T) if b_mn else B
+        Cm, _ = P.gemm_test(0, a_mn, b_mn, M, N, K, 1, Ain, Bin)
+        assert np.array_equal(Cm, ref), (a_mn, b_mn, np.abs(Cm - ref).max())
