@@ -78,6 +78,7 @@ def lib():
     L.dqnb_update.argtypes = [H, C.c_int32, fp, fp]
     L.dqnb_update_with_indices.argtypes = [H, ip, fp, fp]
     L.dqnb_benchmark.argtypes = [H, C.c_int32, fp]
+    L.dqnb_benchmark_gemms.argtypes = [H, C.c_int32, fp, ip]
     L.dqnb_peek_sample_indices.argtypes = [H, ip]
     L.dqnb_select_actions.argtypes = [H, C.c_int32, fp, fp]
     L.dqnb_select_actions_async.argtypes = [H, C.c_int32, fp]
@@ -100,7 +101,8 @@ EXPORTS = [
     "dqnb_param_count", "dqnb_set_params", "dqnb_get_params", "dqnb_init_params", "dqnb_clone_targets",
     "dqnb_set_opt_state", "dqnb_get_opt_state", "dqnb_iters", "dqnb_add_transitions",
     "dqnb_add_transition", "dqnb_memory_size", "dqnb_clear_memory", "dqnb_get_transitions",
-    "dqnb_update", "dqnb_update_with_indices", "dqnb_benchmark", "dqnb_peek_sample_indices",
+    "dqnb_update", "dqnb_update_with_indices", "dqnb_benchmark", "dqnb_benchmark_gemms",
+    "dqnb_peek_sample_indices",
     "dqnb_select_actions", "dqnb_select_actions_async", "dqnb_select_actions_wait", "dqnb_evaluate",
     "dqnb_comm_unique_id", "dqnb_comm_init", "dqnb_sync", "dqnb_kernel_launches", "dqnb_debug_read",
     "dqnb_gemm_test",

@@ -45,7 +45,7 @@ static EncodeTiledFn get_encode() {
 // Split-plane matrix [2][rows][ld] -> 3-D tensor map {ld (inner), rows, 2 planes}, fp32,
 // 128-byte swizzle, box {32, box_rows, 2}; out-of-bounds elements read as zero.
 static int make_tmap(CUtensorMap *tm, const float *base, int rows, int ld, long long plane_elems,
-                     int box_rows) {
+                     int box_rows, bool mn_major) {
   EncodeTiledFn enc = get_encode();
   if (!enc) DQNB_FAIL("cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[3] = {(cuuint64_t)ld, (cuuint64_t)rows, 2};
@@ -53,7 +53,9 @@ static int make_tmap(CUtensorMap *tm, const float *base, int rows, int ld, long 
   cuuint32_t box[3] = {32, (cuuint32_t)box_rows, 2};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)base, dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   // MN-major fp32 operands need the 32-byte-atom flavour of the 128B swizzle (gemm.cuh)
+                   mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) DQNB_FAIL("cuTensorMapEncodeTiled failed with CUresult %d (rows=%d ld=%d)", (int)r, rows, ld);
   return 0;
@@ -305,8 +307,8 @@ static int finish_gemm(const dqnb_config &cfg, Op *op) {
   if (cfg.gemm_mode == DQNB_GEMM_TCGEN05_3XTF32) {
     // A
     const int a_rows = p.a_mn ? p.K : p.M, b_rows = p.b_mn ? p.K : p.N;
-    if (make_tmap(&op->gemm.tmA, p.A, a_rows, p.lda, p.a_plane, p.a_mn ? 32 : BM)) return -1;
-    if (make_tmap(&op->gemm.tmB, p.B, b_rows, p.ldb, p.b_plane, p.b_mn ? 32 : BN)) return -1;
+    if (make_tmap(&op->gemm.tmA, p.A, a_rows, p.lda, p.a_plane, p.a_mn ? 32 : BM, p.a_mn != 0)) return -1;
+    if (make_tmap(&op->gemm.tmB, p.B, b_rows, p.ldb, p.b_plane, p.b_mn ? 32 : BN, p.b_mn != 0)) return -1;
     op->grid = dim3((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, p.splits);
   } else {
     op->grid = dim3((p.N + ST - 1) / ST, (p.M + ST - 1) / ST, p.splits);
@@ -1065,6 +1067,28 @@ int dqnb_benchmark(dqnb_handle h, int32_t n_updates, float *elapsed_ms) {
   DQNB_CUDA(cudaEventRecord(h->ev1, h->stream));
   DQNB_CUDA(cudaEventSynchronize(h->ev1));
   DQNB_CUDA(cudaEventElapsedTime(elapsed_ms, h->ev0, h->ev1));
+  return 0;
+}
+
+// Device time of the dense-layer launches of one update, back to back (bench.py roofline leg).
+int dqnb_benchmark_gemms(dqnb_handle h, int32_t reps, float *ms_per_update, int32_t *gemm_launches) {
+  if (!h || reps <= 0 || !ms_per_update) DQNB_FAIL("bad argument");
+  DQNB_CUDA(cudaSetDevice(h->cfg.device));
+  int n = 0;
+  for (const Op &op : h->update_ops) if (op.kind == Op::GEMM) ++n;
+  DQNB_CUDA(cudaStreamSynchronize(h->stream));
+  for (int r = 0; r < reps + 2; ++r) {
+    if (r == 2) DQNB_CUDA(cudaEventRecord(h->ev0, h->stream));
+    for (const Op &op : h->update_ops)
+      if (op.kind == Op::GEMM && launch_op(h, op, h->stream)) return -1;
+  }
+  DQNB_CUDA(cudaEventRecord(h->ev1, h->stream));
+  DQNB_CUDA(cudaEventSynchronize(h->ev1));
+  float ms = 0.f;
+  DQNB_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  *ms_per_update = ms / reps;
+  if (gemm_launches) *gemm_launches = n;
+  h->launches += (int64_t)n * (reps + 2);
   return 0;
 }
 

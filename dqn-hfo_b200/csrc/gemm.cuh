@@ -159,7 +159,7 @@ constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;   // 48 KB
 constexpr int MN_GROUP_BYTES = 2 * 32 * BK * 4;       // MN-major: one 32-wide group, hi then lo
 constexpr int TC_SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int TC_THREADS = 192;
-constexpr int TMEM_COLS = 64;
+constexpr int TMEM_COLS = 128;   // two fp32 accumulators of BN columns
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
   return (uint32_t)__cvta_generic_to_shared(p);
@@ -214,17 +214,40 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uin
 // UMMA shared-memory matrix descriptor (sm_100): start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46)
 // | version=1 [46,48) | layout_type [61,64) (2 = SWIZZLE_128B).
 //  K-major tile  : rows of 128 B (32 fp32 of K), 8-row swizzle atoms 1024 B apart (SBO); LBO unused.
-//  MN-major tile : 128 B rows hold 32 consecutive M/N elements for one k; 8 k-rows form an atom
-//                  (SBO = 1024 B to the next k-group); LBO = distance between 32-wide M/N groups.
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+//  MN-major tile : 128 B rows hold 32 consecutive M/N elements for one k; 4 k-rows form an atom
+//                  (SBO = 512 B to the next k-group); LBO = distance between 32-wide M/N groups.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                              uint64_t layout_type) {
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) |
-         ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) | (2ull << 61);
+         ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) | (layout_type << 61);
+}
+// K-major operands use SWIZZLE_128B (16-byte swizzle chunks, 8-row atoms).  MN-major operands of a
+// 32-bit type must use the "128B swizzle with 32-byte atomicity" layout (UMMA layout type 1, TMA
+// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): 32-byte chunks XORed with (row % 4), atoms of 4 k-rows.
+constexpr uint64_t kLayoutSW128 = 2, kLayoutSW128Base32B = 1;
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t saddr) { return umma_desc(saddr, 16, 1024, kLayoutSW128); }
+__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t saddr) {
+  // LBO: next 32-wide M/N group; SBO: next group of 4 k-rows (4 x 128 B)
+  return umma_desc(saddr, 2 * 32 * 32 * 4, 512, kLayoutSW128Base32B);
 }
 // instruction descriptor: D=f32 [4,6)=1, A=tf32 [7,10)=2, B=tf32 [10,13)=2, a_major [15], b_major [16],
 // N>>3 [17,23), M>>4 [24,29)
 __device__ __forceinline__ uint32_t umma_idesc_tf32(int a_mn, int b_mn) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
          ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
+        "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]),
+        "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]),
+        "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmArgs args) {
@@ -303,23 +326,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
         for (int ks = 0; ks < BK / 8; ++ks) {
           uint64_t a_hi, a_lo, b_hi, b_lo;
           if (!p.a_mn) {
-            a_hi = umma_desc(sa + ks * 32, 16, 1024);
-            a_lo = umma_desc(sa + A_PLANE_BYTES + ks * 32, 16, 1024);
+            a_hi = desc_kmajor(sa + ks * 32);
+            a_lo = desc_kmajor(sa + A_PLANE_BYTES + ks * 32);
           } else {
-            a_hi = umma_desc(sa + ks * 1024, MN_GROUP_BYTES, 1024);
-            a_lo = umma_desc(sa + 4096 + ks * 1024, MN_GROUP_BYTES, 1024);
+            a_hi = desc_mnmajor(sa + ks * 1024);
+            a_lo = desc_mnmajor(sa + 4096 + ks * 1024);
           }
           if (!p.b_mn) {
-            b_hi = umma_desc(sb + ks * 32, 16, 1024);
-            b_lo = umma_desc(sb + B_PLANE_BYTES + ks * 32, 16, 1024);
+            b_hi = desc_kmajor(sb + ks * 32);
+            b_lo = desc_kmajor(sb + B_PLANE_BYTES + ks * 32);
           } else {
-            b_hi = umma_desc(sb + ks * 1024, MN_GROUP_BYTES, 1024);
-            b_lo = umma_desc(sb + 4096 + ks * 1024, MN_GROUP_BYTES, 1024);
+            b_hi = desc_mnmajor(sb + ks * 1024);
+            b_lo = desc_mnmajor(sb + 4096 + ks * 1024);
           }
-          // small cross terms first, then the dominant hi*hi term
-          tc_mma_tf32(tmem, a_lo, b_hi, idesc, (it > 0 || ks > 0) ? 1u : 0u);
-          tc_mma_tf32(tmem, a_hi, b_lo, idesc, 1u);
-          tc_mma_tf32(tmem, a_hi, b_hi, idesc, 1u);
+          // Two TMEM accumulators: the dominant hi*hi chain and the small cross terms.  The tensor
+          // core truncates when it adds into the fp32 accumulator, so keeping the 2^-11-scaled terms
+          // out of the long chain cuts the accumulated rounding bias ~3x; the epilogue adds the two.
+          const uint32_t first = (it > 0 || ks > 0) ? 1u : 0u;
+          tc_mma_tf32(tmem, a_hi, b_hi, idesc, first);
+          tc_mma_tf32(tmem + BN, a_lo, b_hi, idesc, first);
+          tc_mma_tf32(tmem + BN, a_hi, b_lo, idesc, 1u);
         }
         tc_commit(empty);                  // frees the smem stage when these MMAs retire
       }
@@ -338,21 +364,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
 #pragma unroll
     for (int c0 = 0; c0 < BN; c0 += 32) {
       if (iters > 0) {
-        uint32_t r[32];
+        uint32_t r[32], r2[32];
         const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
-              "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
-              "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
-              "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]),
-              "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-            : "r"(taddr));
+        tmem_ld32(taddr, r);
+        tmem_ld32(taddr + BN, r2);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + __uint_as_float(r2[j]);
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = 0.f;
@@ -363,6 +381,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
+    __syncwarp();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS)
                  : "memory");
   }

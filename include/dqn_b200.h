@@ -120,6 +120,10 @@ int dqnb_update_with_indices(dqnb_handle h, const int32_t *idx, float *critic_lo
 /* Same as dqnb_update but returns the device time of the n updates measured with CUDA events on
  * the handle's stream (the reference's Benchmark(), dqn.cpp:487-498). */
 int dqnb_benchmark(dqnb_handle h, int32_t n_updates, float *elapsed_ms);
+/* Device time (CUDA events) of just the dense-layer launches of one update, averaged over reps:
+ * the live measurement behind bench.py's roofline line.  Leaves learner state untouched except
+ * for scratch activations. */
+int dqnb_benchmark_gemms(dqnb_handle h, int32_t reps, float *ms_per_update, int32_t *gemm_launches);
 /* Draws the indices the next dqnb_update would use, without updating (tests). */
 int dqnb_peek_sample_indices(dqnb_handle h, int32_t *idx);
 

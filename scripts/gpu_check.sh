@@ -4,7 +4,8 @@
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.txt 2>&1
 nproc > gpurun_out/nproc.txt
-echo "== simt gemm" ; timeout 300 python -m pytest tests/test_gpu_gemm.py -x -q -m gpu -k "simt" 2>&1 | tail -15 | tee gpurun_out/t_gemm_simt.log
-echo "== tcgen05 gemm"; timeout 300 python -m pytest tests/test_gpu_gemm.py -q -m gpu -k "tcgen05 or exact" 2>&1 | tail -40 | tee gpurun_out/t_gemm_tc.log
-echo "== update simt"; timeout 900 python -m pytest tests/test_gpu_update.py -q -m gpu -k "simt or ring or sampler" 2>&1 | tail -40 | tee gpurun_out/t_update_simt.log
-echo "== update all"; timeout 1200 python -m pytest tests/test_gpu_update.py -q -m gpu -k "not simt and not ring and not sampler" 2>&1 | tail -40 | tee gpurun_out/t_update_tc.log
+echo "== diag gemm"; timeout 120 python scripts/diag_gemm.py 2>&1 | head -30 | tee gpurun_out/diag_gemm.log
+echo "== gemm"; timeout 300 python -m pytest tests/test_gpu_gemm.py -q -m gpu 2>&1 | tail -25 | tee gpurun_out/t_gemm.log
+echo "== update"; timeout 1200 python -m pytest tests/test_gpu_update.py -q -m gpu 2>&1 | tail -60 | tee gpurun_out/t_update.log
+echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5 | tee gpurun_out/smoke.log
+echo "== bench"; timeout 900 python bench.py --steps 300 --warmup 20 2>&1 | tail -5 | tee gpurun_out/bench.log

@@ -47,8 +47,8 @@ def test_single_update_matches_oracle(S, B, hidden, mode, gemm_mode):
         assert e < RTOL, (k, e, errs)
     cs = compare_state(st, d)
     assert cs["iters"] == (1, 1)
-    assert cs["critic"] < 0.02 * st.cfg.critic_lr + 1e-7, cs
-    assert cs["actor"] < 0.02 * st.cfg.actor_lr + 1e-7, cs
+    assert cs["critic"] < 0.05 * st.cfg.critic_lr + 1e-7, cs
+    assert cs["actor"] < 0.05 * st.cfg.actor_lr + 1e-7, cs
     assert cs["critic_target"] < 1e-6 and cs["actor_target"] < 1e-6, cs
     assert cs["critic_m"] < RTOL and cs["actor_m"] < RTOL, cs
     assert cs["critic_v"] < 2 * RTOL and cs["actor_v"] < 2 * RTOL, cs
