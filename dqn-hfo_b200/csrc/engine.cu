@@ -307,9 +307,10 @@ static int finish_gemm(const dqnb_config &cfg, Op *op) {
   if (cfg.gemm_mode == DQNB_GEMM_TCGEN05_3XTF32) {
     // A
     const int a_rows = p.a_mn ? p.K : p.M, b_rows = p.b_mn ? p.K : p.N;
+    if (p.bn != 64 && p.bn != 128) p.bn = 64;
     if (make_tmap(&op->gemm.tmA, p.A, a_rows, p.lda, p.a_plane, p.a_mn ? 32 : BM, p.a_mn != 0)) return -1;
-    if (make_tmap(&op->gemm.tmB, p.B, b_rows, p.ldb, p.b_plane, p.b_mn ? 32 : BN, p.b_mn != 0)) return -1;
-    op->grid = dim3((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, p.splits);
+    if (make_tmap(&op->gemm.tmB, p.B, b_rows, p.ldb, p.b_plane, p.b_mn ? 32 : p.bn, p.b_mn != 0)) return -1;
+    op->grid = dim3((p.N + p.bn - 1) / p.bn, (p.M + BM - 1) / BM, p.splits);
   } else {
     op->grid = dim3((p.N + ST - 1) / ST, (p.M + ST - 1) / ST, p.splits);
   }
@@ -361,7 +362,7 @@ static int op_dw(const dqnb_config &cfg, const NetGeom &g, int l, const SplitMat
   GemmParams &p = op->gemm.p;
   memset(&p, 0, sizeof(p));
   p.M = L.Np; p.N = L.Kp; p.K = dZl.rows; p.a_mn = 1; p.b_mn = 1; p.epi = EPI_PLAIN;
-  const int tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
+  const int tiles = ((p.M + BM - 1) / BM) * ((p.N + 63) / 64);
   p.splits = pick_splits(tiles, p.K / BK, kGradSplits);
   *splits_out = p.splits;
   p.A = dZl.p; p.a_plane = dZl.plane(); p.lda = dZl.ld;
@@ -391,7 +392,7 @@ static int launch_op(dqnb_handle_s *h, const Op &op, cudaStream_t s) {
   switch (op.kind) {
     case Op::GEMM:
       if (h->cfg.gemm_mode == DQNB_GEMM_TCGEN05_3XTF32)
-        gemm_tc_kernel<<<op.grid, TC_THREADS, TC_SMEM_BYTES, s>>>(op.gemm);
+        tc_kernel_for(op.gemm.p.a_mn, op.gemm.p.b_mn, op.gemm.p.bn)<<<op.grid, TC_THREADS, tc_smem_for(op.gemm.p.bn), s>>>(op.gemm);
       else
         gemm_simt_kernel<<<op.grid, 256, 0, s>>>(op.gemm.p);
       break;
@@ -691,7 +692,7 @@ static int create_impl(const dqnb_config *cfg, dqnb_handle_s *h) {
   DQNB_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   DQNB_CUDA(cudaEventCreate(&h->ev0));
   DQNB_CUDA(cudaEventCreate(&h->ev1));
-  DQNB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+  DQNB_CUDA(tc_prepare_all());
 
   h->S = c.state_size; h->Sp = round_up(c.state_size, 64); h->Kc = round_up(c.state_size + kActorOut, 64);
   h->B = c.batch; h->Bp = round_up(c.batch, 128);
@@ -1234,12 +1235,18 @@ int64_t dqnb_debug_read(dqnb_handle h, const char *name, float *out, int64_t cap
 }
 
 // ----------------------------------- kernel unit test ------------------------------------------
+static long long g_dbg_clk[3];
+void dqnb_gemm_test_clocks(long long *out3) { for (int i = 0; i < 3; ++i) out3[i] = g_dbg_clk[i]; }
+
 int dqnb_gemm_test(int device, int gemm_mode, int a_mn, int b_mn, int M, int N, int K, int splits,
                    const float *A, const float *B, float *C, float *elapsed_ms) {
   if (M % 64 || N % 64 || K % 32 || splits < 1 || splits > kGradSplits) DQNB_FAIL("gemm_test: M,N multiples of 64, K of 32, splits<=8");
   DQNB_CUDA(cudaSetDevice(device));
-  DQNB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+  DQNB_CUDA(tc_prepare_all());
   const size_t na = (size_t)M * K, nb = (size_t)N * K, nc = (size_t)M * N;
+  long long *dclk = nullptr;
+  DQNB_CUDA(cudaMalloc(&dclk, 3 * sizeof(long long)));
+  DQNB_CUDA(cudaMemset(dclk, 0, 3 * sizeof(long long)));
   float *dA, *dB, *dAs, *dBs, *dP, *dC;
   DQNB_CUDA(cudaMalloc(&dA, na * 4)); DQNB_CUDA(cudaMalloc(&dB, nb * 4));
   DQNB_CUDA(cudaMalloc(&dAs, 2 * na * 4)); DQNB_CUDA(cudaMalloc(&dBs, 2 * nb * 4));
@@ -1250,10 +1257,15 @@ int dqnb_gemm_test(int device, int gemm_mode, int a_mn, int b_mn, int M, int N, 
   split_kernel<<<(unsigned)((nb + 255) / 256), 256>>>(dB, dBs, dBs + nb, (long long)nb);
   dqnb_config cfg;
   dqnb_default_config(&cfg);
+  const int dbg = gemm_mode >> 8;
+  gemm_mode &= 0xff;
   cfg.gemm_mode = gemm_mode;
   Op op;
   GemmParams &p = op.gemm.p;
   memset(&p, 0, sizeof(p));
+  p.dbg = dbg & 3;
+  p.bn = (dbg >> 8) ? (dbg >> 8) : 64;
+  p.dbg_clk = dclk;
   p.M = M; p.N = N; p.K = K; p.a_mn = a_mn; p.b_mn = b_mn; p.splits = splits; p.epi = EPI_PLAIN;
   p.A = dAs; p.a_plane = (long long)na; p.lda = a_mn ? M : K;
   p.B = dBs; p.b_plane = (long long)nb; p.ldb = b_mn ? N : K;
@@ -1261,10 +1273,10 @@ int dqnb_gemm_test(int device, int gemm_mode, int a_mn, int b_mn, int M, int N, 
   if (finish_gemm(cfg, &op)) return -1;
   cudaEvent_t e0, e1;
   DQNB_CUDA(cudaEventCreate(&e0)); DQNB_CUDA(cudaEventCreate(&e1));
-  const int reps = 5;
+  const int reps = 20;
   for (int r = 0; r < 1 + reps; ++r) {
     if (r == 1) DQNB_CUDA(cudaEventRecord(e0, 0));
-    if (gemm_mode == DQNB_GEMM_TCGEN05_3XTF32) gemm_tc_kernel<<<op.grid, TC_THREADS, TC_SMEM_BYTES>>>(op.gemm);
+    if (gemm_mode == DQNB_GEMM_TCGEN05_3XTF32) tc_kernel_for(a_mn, b_mn, p.bn)<<<op.grid, TC_THREADS, tc_smem_for(p.bn)>>>(op.gemm);
     else gemm_simt_kernel<<<op.grid, 256>>>(op.gemm.p);
   }
   DQNB_CUDA(cudaEventRecord(e1, 0));
@@ -1276,6 +1288,8 @@ int dqnb_gemm_test(int device, int gemm_mode, int a_mn, int b_mn, int M, int N, 
   sum_planes_kernel<<<(unsigned)((nc + 255) / 256), 256>>>(dP, (long long)nc, splits, dC, (long long)nc);
   DQNB_CUDA(cudaGetLastError());
   DQNB_CUDA(cudaMemcpy(C, dC, nc * 4, cudaMemcpyDeviceToHost));
+  DQNB_CUDA(cudaMemcpy(g_dbg_clk, dclk, sizeof(g_dbg_clk), cudaMemcpyDeviceToHost));
+  cudaFree(dclk);
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   cudaFree(dA); cudaFree(dB); cudaFree(dAs); cudaFree(dBs); cudaFree(dP); cudaFree(dC);
   return 0;

@@ -36,6 +36,9 @@ struct GemmParams {
   const float *bias_hi; const float *bias_lo; // EPI_FWD (nullable)
   const float *mask_hi; const float *mask_lo; int ldmask;  // EPI_DX
   int apply_lrelu;                            // EPI_FWD: 0 for linear layers
+  int bn;                                     // N tile of the tcgen05 kernel: 64 or 128
+  int dbg;                                    // perf experiments (gemm_test only): bit0 skip MMA, bit1 skip TMA
+  long long *dbg_clk;                         // optional: MMA-thread clock64 stamps {start, issued, complete}
 };
 
 struct alignas(64) GemmArgs {
@@ -150,16 +153,23 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmParams p) {
 // ---------------------------------------------------------------------------------------------
 // tcgen05 / TMA / TMEM kernel
 // ---------------------------------------------------------------------------------------------
-constexpr int BM = 128, BN = 64, BK = 32, STAGES = 4;
-constexpr int A_PLANE_BYTES = BM * BK * 4;            // 16 KB: one plane of the A tile
-constexpr int B_PLANE_BYTES = BN * BK * 4;            //  8 KB
-constexpr int A_STAGE_BYTES = 2 * A_PLANE_BYTES;      // hi + lo
-constexpr int B_STAGE_BYTES = 2 * B_PLANE_BYTES;
-constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;   // 48 KB
-constexpr int MN_GROUP_BYTES = 2 * 32 * BK * 4;       // MN-major: one 32-wide group, hi then lo
-constexpr int TC_SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int BM = 128, BK = 32;
 constexpr int TC_THREADS = 192;
-constexpr int TMEM_COLS = 128;   // two fp32 accumulators of BN columns
+constexpr int TC_SMEM_MAX = 232448;                   // 227 KB: the per-CTA maximum on sm_100
+
+template <int BN_>
+struct TcCfg {
+  static constexpr int BN = BN_;
+  static constexpr int A_PLANE_BYTES = BM * BK * 4;            // 16 KB: one plane of the A tile
+  static constexpr int B_PLANE_BYTES = BN_ * BK * 4;           // 8 / 16 KB
+  static constexpr int A_STAGE_BYTES = 2 * A_PLANE_BYTES;      // hi + lo
+  static constexpr int B_STAGE_BYTES = 2 * B_PLANE_BYTES;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;   // 48 / 64 KB
+  static constexpr int STAGES = (TC_SMEM_MAX - 2048) / STAGE_BYTES > 4 ? 4 : (TC_SMEM_MAX - 2048) / STAGE_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int TMEM_COLS = 2 * BN_;                    // two fp32 accumulators of BN columns
+};
+constexpr int MN_GROUP_BYTES = 2 * 32 * BK * 4;       // MN-major: one 32-wide group, hi plane then lo plane
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
   return (uint32_t)__cvta_generic_to_shared(p);
@@ -170,6 +180,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
                : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
@@ -182,6 +195,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "DONE:\n\t"
       "}" ::"r"(bar), "r"(parity)
       : "memory");
+}
+// one lane of a converged warp (deterministic for a given member mask)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred px;\n\t"
+      "elect.sync _|px, 0xFFFFFFFF;\n\t"
+      "selp.u32 %0, 1, 0, px;\n\t"
+      "}" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *tm, int c0, int c1,
                                             int c2, uint32_t bar) {
@@ -212,29 +236,29 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uin
 }
 
 // UMMA shared-memory matrix descriptor (sm_100): start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46)
-// | version=1 [46,48) | layout_type [61,64) (2 = SWIZZLE_128B).
-//  K-major tile  : rows of 128 B (32 fp32 of K), 8-row swizzle atoms 1024 B apart (SBO); LBO unused.
-//  MN-major tile : 128 B rows hold 32 consecutive M/N elements for one k; 4 k-rows form an atom
-//                  (SBO = 512 B to the next k-group); LBO = distance between 32-wide M/N groups.
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
-                                              uint64_t layout_type) {
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) |
-         ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) | (layout_type << 61);
-}
-// K-major operands use SWIZZLE_128B (16-byte swizzle chunks, 8-row atoms).  MN-major operands of a
-// 32-bit type must use the "128B swizzle with 32-byte atomicity" layout (UMMA layout type 1, TMA
-// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): 32-byte chunks XORed with (row % 4), atoms of 4 k-rows.
-constexpr uint64_t kLayoutSW128 = 2, kLayoutSW128Base32B = 1;
-__device__ __forceinline__ uint64_t desc_kmajor(uint32_t saddr) { return umma_desc(saddr, 16, 1024, kLayoutSW128); }
-__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t saddr) {
-  // LBO: next 32-wide M/N group; SBO: next group of 4 k-rows (4 x 128 B)
-  return umma_desc(saddr, 2 * 32 * 32 * 4, 512, kLayoutSW128Base32B);
+// | version=1 [46,48) | layout_type [61,64).
+//  K-major tile  : rows of 128 B (32 fp32 of K), SWIZZLE_128B (type 2, 16-byte chunks XOR row%8),
+//                  8-row atoms 1024 B apart (SBO); LBO unused.  k-step advance: +32 B.
+//  MN-major tile : 128 B rows hold 32 consecutive M/N elements of one k.  32-bit MN-major operands
+//                  must use the 128B swizzle with 32-byte atomicity (type 1; TMA
+//                  CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): atoms of 4 k-rows, SBO = 512 B to the next
+//                  k-group, LBO = distance between 32-wide M/N groups.  k-step (8 rows): +1024 B.
+template <int MN>
+struct DescHi {   // the constant upper 32 bits and the LBO part of the lower 32 bits
+  static constexpr uint32_t hi = MN ? ((512u >> 4) | (1u << 14) | (1u << 29))      // SBO 512, v1, type 1
+                                    : ((1024u >> 4) | (1u << 14) | (2u << 29));    // SBO 1024, v1, type 2
+  static constexpr uint32_t lbo = MN ? ((uint32_t)(MN_GROUP_BYTES >> 4) << 16) : (1u << 16);
+  static constexpr uint32_t kstep = MN ? (1024u >> 4) : (32u >> 4);                // per 8 of K
+};
+template <int MN>
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  return ((uint64_t)DescHi<MN>::hi << 32) | (uint64_t)(((saddr & 0x3FFFFu) >> 4) | DescHi<MN>::lbo);
 }
 // instruction descriptor: D=f32 [4,6)=1, A=tf32 [7,10)=2, B=tf32 [10,13)=2, a_major [15], b_major [16],
 // N>>3 [17,23), M>>4 [24,29)
-__device__ __forceinline__ uint32_t umma_idesc_tf32(int a_mn, int b_mn) {
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int a_mn, int b_mn, int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
-         ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
@@ -250,14 +274,22 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr));
 }
 
+// The warp roles run with the whole warp converged: every value feeding TMA / MMA issue is
+// warp-uniform (uniform registers, no per-thread descriptor arithmetic), and one elected lane
+// issues.  A single divergent thread doing that arithmetic costs ~300 cycles per k-step, 3x the
+// tensor time of the three MMAs it feeds (measured: profiles/r01_gemm_issue_loop.md).
+template <int A_MN, int B_MN, int BN_>
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmArgs args) {
+  using Cfg = TcCfg<BN_>;
+  constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   const GemmParams &p = args.p;
   const uint32_t raw = smem_u32(smem_raw);
-  const uint32_t base = (raw + 1023u) & ~1023u;          // SWIZZLE_128B atoms need 1024 B alignment
+  const uint32_t base = (raw + 1023u) & ~1023u;          // swizzle atoms need 1024 B alignment
   uint8_t *base_ptr = smem_raw + (base - raw);
-  const uint32_t bars = base + STAGES * STAGE_BYTES;     // full[STAGES], empty[STAGES], tmem_full
-  volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(base_ptr + STAGES * STAGE_BYTES + 128);
+  const uint32_t bars = base + STAGES * Cfg::STAGE_BYTES;   // full[STAGES], empty[STAGES], tmem_full
+  volatile uint32_t *tmem_slot =
+      reinterpret_cast<volatile uint32_t *>(base_ptr + STAGES * Cfg::STAGE_BYTES + 128);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tile = blockIdx.x, m_tile = blockIdx.y, split = blockIdx.z;
   const int kblocks = p.K / BK;
@@ -265,6 +297,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
   const int kb0 = split * per;
   const int kb1 = min(kblocks, kb0 + per);
   const int iters = max(kb1 - kb0, 0);
+  const uint32_t tfull = bars + 8 * (2 * STAGES);
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&args.tmA) : "memory");
@@ -275,7 +308,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      smem_u32((const void *)tmem_slot)),
-                 "n"(TMEM_COLS)
+                 "n"(Cfg::TMEM_COLS)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -285,75 +318,82 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ---------------- TMA producer ----------------
-      for (int it = 0; it < iters; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-        const uint32_t full = bars + 8 * s, empty = bars + 8 * (STAGES + s);
-        mbar_wait(empty, ph ^ 1u);
-        mbar_expect_tx(full, STAGE_BYTES);
-        const uint32_t sa = base + s * STAGE_BYTES, sb = sa + A_STAGE_BYTES;
-        const int k0 = (kb0 + it) * BK;
-        if (!p.a_mn) {
-          tma_load_3d(sa, &args.tmA, k0, m_tile * BM, 0, full);              // box {32, 128, 2}
+    // ---------------- TMA producer ----------------
+    for (int it = 0; it < iters; ++it) {
+      const int s = it % STAGES;
+      const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+      const uint32_t full = bars + 8 * s, empty = bars + 8 * (STAGES + s);
+      mbar_wait(empty, ph ^ 1u);
+      if (elect_one()) {
+        if (p.dbg & 2) {   // experiment: no loads, just hand the (stale) stage to the MMA warp
+          mbar_arrive(full);
         } else {
+          mbar_expect_tx(full, Cfg::STAGE_BYTES);
+          const uint32_t sa = base + s * Cfg::STAGE_BYTES, sb = sa + Cfg::A_STAGE_BYTES;
+          const int k0 = (kb0 + it) * BK;
+          if (!A_MN) {
+            tma_load_3d(sa, &args.tmA, k0, m_tile * BM, 0, full);              // box {32, 128, 2}
+          } else {
 #pragma unroll
-          for (int g = 0; g < BM / 32; ++g)                                   // box {32, 32, 2}
-            tma_load_3d(sa + g * MN_GROUP_BYTES, &args.tmA, m_tile * BM + g * 32, k0, 0, full);
-        }
-        if (!p.b_mn) {
-          tma_load_3d(sb, &args.tmB, k0, n_tile * BN, 0, full);              // box {32, 64, 2}
-        } else {
+            for (int g = 0; g < BM / 32; ++g)                                   // box {32, 32, 2}
+              tma_load_3d(sa + g * MN_GROUP_BYTES, &args.tmA, m_tile * BM + g * 32, k0, 0, full);
+          }
+          if (!B_MN) {
+            tma_load_3d(sb, &args.tmB, k0, n_tile * BN_, 0, full);             // box {32, BN, 2}
+          } else {
 #pragma unroll
-          for (int g = 0; g < BN / 32; ++g)
-            tma_load_3d(sb + g * MN_GROUP_BYTES, &args.tmB, n_tile * BN + g * 32, k0, 0, full);
+            for (int g = 0; g < BN_ / 32; ++g)
+              tma_load_3d(sb + g * MN_GROUP_BYTES, &args.tmB, n_tile * BN_ + g * 32, k0, 0, full);
+          }
         }
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ---------------- MMA issuer (one thread) ----------------
-      const uint32_t idesc = umma_idesc_tf32(p.a_mn, p.b_mn);
-      for (int it = 0; it < iters; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-        const uint32_t full = bars + 8 * s, empty = bars + 8 * (STAGES + s);
-        mbar_wait(full, ph);
-        tc_fence_after();
-        const uint32_t sa = base + s * STAGE_BYTES, sb = sa + A_STAGE_BYTES;
+    // ---------------- MMA issuer ----------------
+    constexpr uint32_t idesc = umma_idesc_tf32(A_MN, B_MN, BN_);
+    constexpr uint32_t a_lo_off = A_MN ? 4096u : (uint32_t)Cfg::A_PLANE_BYTES;
+    constexpr uint32_t b_lo_off = B_MN ? 4096u : (uint32_t)Cfg::B_PLANE_BYTES;
+    const long long clk0 = p.dbg_clk ? clock64() : 0;
+    for (int it = 0; it < iters; ++it) {
+      const int s = it % STAGES;
+      const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+      const uint32_t full = bars + 8 * s, empty = bars + 8 * (STAGES + s);
+      mbar_wait(full, ph);
+      tc_fence_after();
+      const uint32_t sa = base + s * Cfg::STAGE_BYTES, sb = sa + Cfg::A_STAGE_BYTES;
+      const uint64_t a_hi = make_desc<A_MN>(sa), a_lo = make_desc<A_MN>(sa + a_lo_off);
+      const uint64_t b_hi = make_desc<B_MN>(sb), b_lo = make_desc<B_MN>(sb + b_lo_off);
+      if (elect_one()) {
+        if (!(p.dbg & 1)) {
 #pragma unroll
-        for (int ks = 0; ks < BK / 8; ++ks) {
-          uint64_t a_hi, a_lo, b_hi, b_lo;
-          if (!p.a_mn) {
-            a_hi = desc_kmajor(sa + ks * 32);
-            a_lo = desc_kmajor(sa + A_PLANE_BYTES + ks * 32);
-          } else {
-            a_hi = desc_mnmajor(sa + ks * 1024);
-            a_lo = desc_mnmajor(sa + 4096 + ks * 1024);
+          for (int ks = 0; ks < BK / 8; ++ks) {
+            const uint64_t ka = (uint64_t)(ks * DescHi<A_MN>::kstep), kb = (uint64_t)(ks * DescHi<B_MN>::kstep);
+            // Two TMEM accumulators: the dominant hi*hi chain and the small cross terms.  The tensor
+            // core truncates when it adds into the fp32 accumulator, so keeping the 2^-11-scaled
+            // terms out of the long chain cuts the accumulated rounding bias ~3x; the epilogue adds
+            // the two.
+            const uint32_t first = (it > 0 || ks > 0) ? 1u : 0u;
+            tc_mma_tf32(tmem, a_hi + ka, b_hi + kb, idesc, first);
+            tc_mma_tf32(tmem + BN_, a_lo + ka, b_hi + kb, idesc, first);
+            tc_mma_tf32(tmem + BN_, a_hi + ka, b_lo + kb, idesc, 1u);
           }
-          if (!p.b_mn) {
-            b_hi = desc_kmajor(sb + ks * 32);
-            b_lo = desc_kmajor(sb + B_PLANE_BYTES + ks * 32);
-          } else {
-            b_hi = desc_mnmajor(sb + ks * 1024);
-            b_lo = desc_mnmajor(sb + 4096 + ks * 1024);
-          }
-          // Two TMEM accumulators: the dominant hi*hi chain and the small cross terms.  The tensor
-          // core truncates when it adds into the fp32 accumulator, so keeping the 2^-11-scaled terms
-          // out of the long chain cuts the accumulated rounding bias ~3x; the epilogue adds the two.
-          const uint32_t first = (it > 0 || ks > 0) ? 1u : 0u;
-          tc_mma_tf32(tmem, a_hi, b_hi, idesc, first);
-          tc_mma_tf32(tmem + BN, a_lo, b_hi, idesc, first);
-          tc_mma_tf32(tmem + BN, a_hi, b_lo, idesc, 1u);
         }
         tc_commit(empty);                  // frees the smem stage when these MMAs retire
       }
-      tc_commit(bars + 8 * (2 * STAGES));  // accumulator complete -> epilogue
+      __syncwarp();
     }
+    if (elect_one()) {
+      tc_commit(tfull);                    // accumulators complete -> epilogue
+      if (p.dbg_clk && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+        const long long clk1 = clock64();
+        mbar_wait(tfull, 0);
+        p.dbg_clk[0] = clk0; p.dbg_clk[1] = clk1; p.dbg_clk[2] = clock64();
+      }
+    }
+    __syncwarp();
   } else {
     // ---------------- epilogue: TMEM -> registers -> HBM ----------------
-    const uint32_t tfull = bars + 8 * (2 * STAGES);
     const int q = warp & 3;                // TMEM lane quarter this warp may read
     const int row = m_tile * BM + q * 32 + lane;
     float v[32];
@@ -361,13 +401,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       mbar_wait(tfull, 0);
       tc_fence_after();
     }
-#pragma unroll
-    for (int c0 = 0; c0 < BN; c0 += 32) {
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN_; c0 += 32) {
       if (iters > 0) {
         uint32_t r[32], r2[32];
         const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
         tmem_ld32(taddr, r);
-        tmem_ld32(taddr + BN, r2);
+        tmem_ld32(taddr + BN_, r2);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + __uint_as_float(r2[j]);
@@ -375,16 +415,42 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = 0.f;
       }
-      epi_store<32>(p, row, n_tile * BN + c0, v, split);
+      epi_store<32>(p, row, n_tile * BN_ + c0, v, split);
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     __syncwarp();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(Cfg::TMEM_COLS)
                  : "memory");
   }
+}
+
+// host-side dispatch over the template instances
+typedef void (*TcKernel)(const GemmArgs);
+inline TcKernel tc_kernel_for(int a_mn, int b_mn, int bn) {
+  if (bn == 128) {
+    if (!a_mn && !b_mn) return gemm_tc_kernel<0, 0, 128>;
+    if (!a_mn && b_mn) return gemm_tc_kernel<0, 1, 128>;
+    if (a_mn && !b_mn) return gemm_tc_kernel<1, 0, 128>;
+    return gemm_tc_kernel<1, 1, 128>;
+  }
+  if (!a_mn && !b_mn) return gemm_tc_kernel<0, 0, 64>;
+  if (!a_mn && b_mn) return gemm_tc_kernel<0, 1, 64>;
+  if (a_mn && !b_mn) return gemm_tc_kernel<1, 0, 64>;
+  return gemm_tc_kernel<1, 1, 64>;
+}
+inline int tc_smem_for(int bn) { return bn == 128 ? TcCfg<128>::SMEM_BYTES : TcCfg<64>::SMEM_BYTES; }
+inline cudaError_t tc_prepare_all() {
+  for (int bn : {64, 128})
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 2; ++b) {
+        cudaError_t e = cudaFuncSetAttribute((const void *)tc_kernel_for(a, b, bn),
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_for(bn));
+        if (e != cudaSuccess) return e;
+      }
+  return cudaSuccess;
 }
 
 }  // namespace dqnb

@@ -32,6 +32,7 @@ int dqo_load_blas(const char *path) {
   void *h = dlopen(path, RTLD_NOW | RTLD_LOCAL);
   if (!h) return -1;
   cblas_sgemm_fn f = (cblas_sgemm_fn)dlsym(h, "cblas_sgemm");
+  if (!f) f = (cblas_sgemm_fn)dlsym(h, "scipy_cblas_sgemm"); /* scipy's bundled OpenBLAS (LP64) */
   if (!f) { dlclose(h); return -2; }
   g_blas_handle = h;
   g_sgemm = f;
@@ -42,6 +43,7 @@ void dqo_set_threads(int n) {
   g_threads = n;
   if (g_blas_handle) {
     void (*set)(int) = (void (*)(int))dlsym(g_blas_handle, "openblas_set_num_threads");
+    if (!set) set = (void (*)(int))dlsym(g_blas_handle, "scipy_openblas_set_num_threads");
     if (set && n > 0) set(n);
   }
 }

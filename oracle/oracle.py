@@ -114,24 +114,32 @@ def make_config(state_size=58, batch=32, hidden=(1024, 512, 256, 128), gamma=0.9
     return c
 
 
-def find_openblas() -> str | None:
+def find_openblas() -> list:
     """An in-image OpenBLAS exporting cblas_sgemm (used only for the timed CPU baseline)."""
     import site
     pats = []
     for sp in site.getsitepackages():
-        pats += [os.path.join(sp, "opencv_python_headless.libs", "libopenblas*.so*"),
-                 os.path.join(sp, "scipy.libs", "libscipy_openblas-*.so*")]
+        pats += [os.path.join(sp, "scipy.libs", "libscipy_openblas-*.so*"),          # scipy_cblas_sgemm, LP64
+                 os.path.join(sp, "opencv_python_headless.libs", "libopenblas*.so*")]
+    out = []
     for p in pats:
-        for f in sorted(glob.glob(p)):
-            return f
-    return None
+        out += sorted(glob.glob(p))
+    return out
+
+
+_blas_loaded = False
 
 
 def load_blas() -> bool:
-    p = find_openblas()
-    if p is None:
-        return False
-    return lib().dqo_load_blas(p.encode()) == 0
+    """dlopen()s the first in-image OpenBLAS that exports (scipy_)cblas_sgemm with 32-bit ints."""
+    global _blas_loaded
+    if _blas_loaded:
+        return True
+    for p in find_openblas():
+        if lib().dqo_load_blas(p.encode()) == 0:
+            _blas_loaded = True
+            return True
+    return False
 
 
 @dataclass
