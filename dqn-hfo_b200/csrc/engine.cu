@@ -8,13 +8,14 @@
 #include <string.h>
 
 #include <algorithm>
+#include <utility>
 #include <random>
 #include <string>
 #include <vector>
 
 #include "common.cuh"
-#include "gemm.cuh"
 #include "kernels.cuh"
+#include "gemm.cuh"
 
 namespace dqnb {
 
@@ -209,7 +210,8 @@ struct SplitMat {           // [2][rows][ld] fp32 in HBM
 
 struct Op {                 // one kernel launch of the update / act sequence
   enum Kind { GEMM, GATHER, SAMPLE, HEAD_FWD, QK, HEAD_BWD_X, HEAD_BWD_W, COLSUM, INVERT, REDUCE,
-              ALLREDUCE, ADAM, PREP, FINALIZE } kind;
+              ALLREDUCE, ADAM, PREP, FINALIZE, FORK, JOIN } kind;
+  int branch = 0;           // 0 = main stream; 1, 2 = side streams between FORK and JOIN
   GemmArgs gemm; dim3 grid;
   GatherArgs gather; HeadArgs head; QArgs q; HeadBwdXArgs hbx; HeadBwdWArgs hbw; ColsumArgs cs;
   InvertArgs inv; ReduceArgs red; AdamArgs adam;
@@ -226,6 +228,8 @@ struct dqnb_handle_s {
   int S, Sp, Kc, B, Bp, An /*act rows pad*/;
   NetGeom gA, gC;
   cudaStream_t stream = nullptr;
+  cudaStream_t side[2] = {nullptr, nullptr};          // independent forward chains run beside the main one
+  cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::vector<void *> allocs;
   std::vector<void *> pinned;
@@ -244,7 +248,7 @@ struct dqnb_handle_s {
   SplitMat Xs, Xsn, Xc, Xct, Xcp;
   float *reward = nullptr, *mc = nullptr, *term = nullptr, *y = nullptr;
   float *q_next = nullptr, *q = nullptr, *q_pi = nullptr;
-  float *q16 = nullptr, *a16_t = nullptr, *a16_pi = nullptr, *d16c = nullptr, *d16a = nullptr;
+  float *q16 = nullptr, *q16c = nullptr, *a16_t = nullptr, *a16_pi = nullptr, *d16c = nullptr, *d16a = nullptr;
   float *d_in = nullptr, *tap_raw = nullptr, *tap_inv = nullptr;
   SplitMat actAT[DQNB_MAX_HIDDEN], actCT[DQNB_MAX_HIDDEN], actC[DQNB_MAX_HIDDEN], actA[DQNB_MAX_HIDDEN], dZ[DQNB_MAX_HIDDEN];
   // act path
@@ -386,30 +390,52 @@ static void op_head_fwd(const NetGeom &g, const float *P, const SplitMat &H, int
 }  // namespace dqnb
 
 // ---------------------------------------------------------------------------------------------
-// launching
+// launching: every kernel goes out with the programmatic-stream-serialization attribute (PDL);
+// the kernels call griddepcontrol.wait before touching global memory (kernels.cuh).
 // ---------------------------------------------------------------------------------------------
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                            Args &&...args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+
 static int launch_op(dqnb_handle_s *h, const Op &op, cudaStream_t s) {
+  cudaError_t e = cudaSuccess;
   switch (op.kind) {
     case Op::GEMM:
       if (h->cfg.gemm_mode == DQNB_GEMM_TCGEN05_3XTF32)
-        tc_kernel_for(op.gemm.p.a_mn, op.gemm.p.b_mn, op.gemm.p.bn)<<<op.grid, TC_THREADS, tc_smem_for(op.gemm.p.bn), s>>>(op.gemm);
+        e = launch_k(tc_kernel_for(op.gemm.p.a_mn, op.gemm.p.b_mn, op.gemm.p.bn), op.grid, dim3(TC_THREADS),
+                     (size_t)tc_smem_for(op.gemm.p.bn), s, op.gemm);
       else
-        gemm_simt_kernel<<<op.grid, 256, 0, s>>>(op.gemm.p);
+        e = launch_k(gemm_simt_kernel, op.grid, dim3(256), 0, s, op.gemm.p);
       break;
-    case Op::GATHER: gather_kernel<<<h->Bp, 128, 0, s>>>(op.gather); break;
-    case Op::SAMPLE: sample_kernel<<<(h->B + 255) / 256, 256, 0, s>>>(h->st, h->cfg.seed, h->B, h->idx); break;
-    case Op::HEAD_FWD: head_fwd_kernel<<<op.blocks, 256, 0, s>>>(op.head); break;
-    case Op::QK: q_kernel<<<op.blocks, 256, 0, s>>>(op.q); break;
-    case Op::HEAD_BWD_X: head_bwd_x_kernel<<<op.blocks, 256, 0, s>>>(op.hbx); break;
-    case Op::HEAD_BWD_W: head_bwd_w_kernel<<<op.grid, 512, 0, s>>>(op.hbw); break;
-    case Op::COLSUM: colsum_kernel<<<op.grid, 512, 0, s>>>(op.cs); break;
-    case Op::INVERT: invert_kernel<<<op.blocks, 256, 0, s>>>(op.inv); break;
-    case Op::REDUCE: reduce_kernel<<<op.blocks, 256, 0, s>>>(op.red); break;
-    case Op::ADAM: adam_kernel<<<op.blocks, 256, 0, s>>>(op.adam); break;
-    case Op::PREP: prep_kernel<<<1, 32, 0, s>>>(h->st, h->hp); break;
+    case Op::GATHER: e = launch_k(gather_kernel, dim3(h->Bp), dim3(128), 0, s, op.gather); break;
+    case Op::SAMPLE:
+      e = launch_k(sample_kernel, dim3((h->B + 255) / 256), dim3(256), 0, s, (const StepState *)h->st,
+                   (unsigned long long)h->cfg.seed, h->B, h->idx);
+      break;
+    case Op::HEAD_FWD: e = launch_k(head_fwd_kernel, dim3(op.blocks), dim3(256), 0, s, op.head); break;
+    case Op::QK: e = launch_k(q_kernel, dim3(op.blocks), dim3(256), 0, s, op.q); break;
+    case Op::HEAD_BWD_X: e = launch_k(head_bwd_x_kernel, dim3(op.blocks), dim3(256), 0, s, op.hbx); break;
+    case Op::HEAD_BWD_W: e = launch_k(head_bwd_w_kernel, op.grid, dim3(512), 0, s, op.hbw); break;
+    case Op::COLSUM: e = launch_k(colsum_kernel, op.grid, dim3(512), 0, s, op.cs); break;
+    case Op::INVERT: e = launch_k(invert_kernel, dim3(op.blocks), dim3(256), 0, s, op.inv); break;
+    case Op::REDUCE: e = launch_k(reduce_kernel, dim3(op.blocks), dim3(256), 0, s, op.red); break;
+    case Op::ADAM: e = launch_k(adam_kernel, dim3(op.blocks), dim3(256), 0, s, op.adam); break;
+    case Op::PREP: e = launch_k(prep_kernel, dim3(1), dim3(32), 0, s, h->st, h->hp); break;
     case Op::FINALIZE:
-      finalize_kernel<<<1, 32, 0, s>>>(h->st, h->G[1] + h->gC.flat, h->G[0] + h->gA.flat, h->results, h->max_slots);
+      e = launch_k(finalize_kernel, dim3(1), dim3(32), 0, s, h->st, (const float *)(h->G[1] + h->gC.flat),
+                   (const float *)(h->G[0] + h->gA.flat), h->results, h->max_slots);
       break;
+    case Op::FORK:
+    case Op::JOIN:
+      return 0;   // stream plumbing, handled by run_ops
     case Op::ALLREDUCE: {
       if (!h->comm) DQNB_FAIL("world_size > 1 but dqnb_comm_init was not called");
       int r = nccl().AllReduce(op.ar_buf, op.ar_buf, op.ar_count, kNcclFloat, kNcclSum, h->comm, s);
@@ -417,7 +443,7 @@ static int launch_op(dqnb_handle_s *h, const Op &op, cudaStream_t s) {
       return 0;
     }
   }
-  DQNB_CUDA(cudaGetLastError());
+  DQNB_CUDA(e);
   return 0;
 }
 
@@ -425,7 +451,19 @@ static int run_ops(dqnb_handle_s *h, const std::vector<Op> &ops, cudaStream_t s,
   int n = 0;
   for (const Op &op : ops) {
     if (skip_sample && op.kind == Op::SAMPLE) continue;
-    if (launch_op(h, op, s)) return -1;
+    if (op.kind == Op::FORK) {          // side streams pick up after everything queued on the main one
+      DQNB_CUDA(cudaEventRecord(h->ev_fork, s));
+      for (int b = 0; b < 2; ++b) DQNB_CUDA(cudaStreamWaitEvent(h->side[b], h->ev_fork, 0));
+      continue;
+    }
+    if (op.kind == Op::JOIN) {
+      for (int b = 0; b < 2; ++b) {
+        DQNB_CUDA(cudaEventRecord(h->ev_join[b], h->side[b]));
+        DQNB_CUDA(cudaStreamWaitEvent(s, h->ev_join[b], 0));
+      }
+      continue;
+    }
+    if (launch_op(h, op, op.branch ? h->side[op.branch - 1] : s)) return -1;
     if (op.kind != Op::ALLREDUCE) ++n;
   }
   if (count) *count = n;
@@ -525,12 +563,12 @@ static void build_solver(dqnb_handle_s *h, int is_critic, const SegTable &segs, 
   ops.push_back(ad);
 }
 
-static void push_q(dqnb_handle_s *h, int mode, float *q_tap, float *d16, std::vector<Op> &ops) {
+static void push_q(dqnb_handle_s *h, int mode, const float *q16, float *q_tap, float *d16, std::vector<Op> &ops) {
   Op op;
   op.kind = Op::QK;
   QArgs &a = op.q;
   memset(&a, 0, sizeof(a));
-  a.mode = mode; a.B = h->B; a.q16 = h->q16; a.reward = h->reward; a.mc = h->mc; a.term = h->term;
+  a.mode = mode; a.B = h->B; a.q16 = q16; a.reward = h->reward; a.mc = h->mc; a.term = h->term;
   a.y = h->y; a.q_tap = q_tap; a.d16 = d16; a.part = h->scal_part; a.hp = h->hp;
   op.blocks = (h->B + 255) / 256;
   ops.push_back(op);
@@ -578,25 +616,39 @@ static int build_update_ops(dqnb_handle_s *h) {
     a.reward = h->reward; a.mc = h->mc; a.term = h->term;
   }
   ops.push_back(op);
-  // dqn.cpp:889-891 CriticForwardThroughActor(critic_target, actor_target, s')
+  // Three independent forward chains run side by side (separate streams -> parallel graph branches):
+  //   main  : dqn.cpp:889-891 CriticForwardThroughActor(critic_target, actor_target, s') + TD target
+  //   side 1: forward half of critic_solver_->Step(1) on (s, a, p)            (dqn.cpp:904)
+  //   side 2: actor forward on s with the pre-update actor                    (dqn.cpp:910-911)
+  op.kind = Op::FORK; ops.push_back(op);
+  {
+    const size_t mark = ops.size();
+    if (build_forward(h, gC, PC, h->Xc, h->actC, ops)) return -1;
+    op_head_fwd(gC, PC, h->actC[topC], h->B, h->q16c, nullptr, 0, &op); ops.push_back(op);
+    for (size_t i = mark; i < ops.size(); ++i) ops[i].branch = 1;
+  }
+  {
+    const size_t mark = ops.size();
+    if (build_forward(h, gA, PA, h->Xs, h->actA, ops)) return -1;
+    op_head_fwd(gA, PA, h->actA[topA], h->B, h->a16_pi, &h->Xcp, h->S, &op); ops.push_back(op);
+    for (size_t i = mark; i < ops.size(); ++i) ops[i].branch = 2;
+  }
+  op.branch = 0;
   if (build_forward(h, gA, PAT, h->Xsn, h->actAT, ops)) return -1;
   op_head_fwd(gA, PAT, h->actAT[topA], h->B, h->a16_t, &h->Xct, h->S, &op); ops.push_back(op);
   if (build_forward(h, gC, PCT, h->Xct, h->actCT, ops)) return -1;
   op_head_fwd(gC, PCT, h->actCT[topC], h->B, h->q16, nullptr, 0, &op); ops.push_back(op);
-  push_q(h, QMODE_TARGET, h->q_next, nullptr, ops);              // dqn.cpp:892-900
-  // dqn.cpp:904 critic_solver_->Step(1)
-  if (build_forward(h, gC, PC, h->Xc, h->actC, ops)) return -1;
-  op_head_fwd(gC, PC, h->actC[topC], h->B, h->q16, nullptr, 0, &op); ops.push_back(op);
-  push_q(h, QMODE_LOSS, h->q, h->d16c, ops);
+  push_q(h, QMODE_TARGET, h->q16, h->q_next, nullptr, ops);      // dqn.cpp:892-900
+  op.kind = Op::JOIN; ops.push_back(op);
+  // rest of critic_solver_->Step(1): loss, backward, clip, Adam (+ soft update of the target critic)
+  push_q(h, QMODE_LOSS, h->q16c, h->q, h->d16c, ops);
   push_head_bwd(h, gC, PC, h->d16c, h->actC[topC], true, ops);
   if (build_backward(h, gC, PC, h->Xc, h->actC, true, &h->segs[1], ops)) return -1;
   build_solver(h, 1, h->segs[1], 0.5f * h->hp.inv_batch_global, ops);
-  // dqn.cpp:910-916 actor forward, critic forward with the updated critic
-  if (build_forward(h, gA, PA, h->Xs, h->actA, ops)) return -1;
-  op_head_fwd(gA, PA, h->actA[topA], h->B, h->a16_pi, &h->Xcp, h->S, &op); ops.push_back(op);
+  // dqn.cpp:913-916 critic forward on (s, a_pi) with the updated critic
   if (build_forward(h, gC, PC, h->Xcp, h->actC, ops)) return -1;
   op_head_fwd(gC, PC, h->actC[topC], h->B, h->q16, nullptr, 0, &op); ops.push_back(op);
-  push_q(h, QMODE_POLICY, h->q_pi, h->d16c, ops);                // dqn.cpp:918-921
+  push_q(h, QMODE_POLICY, h->q16, h->q_pi, h->d16c, ops);        // dqn.cpp:918-921
   // dqn.cpp:923 critic.BackwardFrom(q_values_layer): only the input diff is consumed
   push_head_bwd(h, gC, PC, h->d16c, h->actC[topC], false, ops);
   if (build_backward(h, gC, PC, h->Xcp, h->actC, false, nullptr, ops)) return -1;
@@ -666,6 +718,11 @@ int dqnb_destroy(dqnb_handle h) {
   if (h->comm && nccl().CommDestroy) nccl().CommDestroy(h->comm);
   for (void *p : h->allocs) cudaFree(p);
   for (void *p : h->pinned) cudaFreeHost(p);
+  for (int b = 0; b < 2; ++b) {
+    if (h->ev_join[b]) cudaEventDestroy(h->ev_join[b]);
+    if (h->side[b]) cudaStreamDestroy(h->side[b]);
+  }
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -692,6 +749,11 @@ static int create_impl(const dqnb_config *cfg, dqnb_handle_s *h) {
   DQNB_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   DQNB_CUDA(cudaEventCreate(&h->ev0));
   DQNB_CUDA(cudaEventCreate(&h->ev1));
+  for (int b = 0; b < 2; ++b) {
+    DQNB_CUDA(cudaStreamCreateWithFlags(&h->side[b], cudaStreamNonBlocking));
+    DQNB_CUDA(cudaEventCreateWithFlags(&h->ev_join[b], cudaEventDisableTiming));
+  }
+  DQNB_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
   DQNB_CUDA(tc_prepare_all());
 
   h->S = c.state_size; h->Sp = round_up(c.state_size, 64); h->Kc = round_up(c.state_size + kActorOut, 64);
@@ -722,7 +784,7 @@ static int create_impl(const dqnb_config *cfg, dqnb_handle_s *h) {
   float **vecs[] = {&h->reward, &h->mc, &h->term, &h->y, &h->q_next, &h->q, &h->q_pi};
   for (float **v : vecs) if (dalloc(h, v, (size_t)h->Bp)) return -1;
   const int rows16 = std::max(h->Bp, h->An);
-  float **m16[] = {&h->q16, &h->a16_t, &h->a16_pi, &h->d16c, &h->d16a, &h->out16_act};
+  float **m16[] = {&h->q16, &h->q16c, &h->a16_t, &h->a16_pi, &h->d16c, &h->d16a, &h->out16_act};
   for (float **v : m16) if (dalloc(h, v, (size_t)rows16 * 16)) return -1;
   if (dalloc(h, &h->d_in, (size_t)h->Bp * h->Kc) || dalloc(h, &h->tap_raw, (size_t)h->Bp * kActorOut) || dalloc(h, &h->tap_inv, (size_t)h->Bp * kActorOut)) return -1;
   for (int l = 0; l < c.n_hidden; ++l) {

@@ -17,6 +17,7 @@
 // gemm_simt_kernel : plain FFMA tiles over the same operands/epilogues (verification mode).
 #pragma once
 #include "common.cuh"
+#include "kernels.cuh"
 
 namespace dqnb {
 
@@ -103,6 +104,7 @@ __device__ __forceinline__ void epi_store(const GemmParams &p, int m, int n0, co
 constexpr int ST = 64, SK = 16;
 
 __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmParams p) {
+  DQNB_PDL_PROLOGUE();
   __shared__ float As[SK][ST + 4];
   __shared__ float Bs[SK][ST + 4];
   const int tid = threadIdx.x;
@@ -316,6 +318,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  // Everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps the tail of the
+  // previous kernel; from here on we read what it wrote.
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ---------------- TMA producer ----------------

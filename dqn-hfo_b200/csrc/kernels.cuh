@@ -7,6 +7,14 @@
 
 namespace dqnb {
 
+// Programmatic dependent launch: every kernel of the update sequence is launched with the
+// programmatic-stream-serialization attribute, so its CTAs may start (and run their prologue)
+// before the previous kernel has drained.  pdl_wait() blocks until the prerequisite grid has
+// completed and its writes are visible; nothing before it may touch global memory.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#define DQNB_PDL_PROLOGUE() do { pdl_wait(); pdl_launch_dependents(); } while (0)
+
 constexpr int kGradSplits = 8;      // planes of the gradient-partial buffer
 constexpr int kMaxSegs = 2 * 8 + 4; // parameter blobs per net
 
@@ -31,6 +39,7 @@ struct HyperParams {
 
 // -------------------------------------------------------------------------------------------
 __global__ void prep_kernel(StepState *st, HyperParams hp) {
+  DQNB_PDL_PROLOGUE();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   // AdamSolver::ComputeUpdateValue: t = iter + 1; correction evaluated in double (std::pow(float,int))
   const int tc = st->critic_iter + 1, ta = st->actor_iter + 1;
@@ -45,6 +54,7 @@ __global__ void prep_kernel(StepState *st, HyperParams hp) {
 
 __global__ void finalize_kernel(StepState *st, const float *g_critic_tail, const float *g_actor_tail,
                                 float *results, int max_slots) {
+  DQNB_PDL_PROLOGUE();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const int slot = st->result_slot;
   if (slot < max_slots) {
@@ -59,6 +69,7 @@ __global__ void finalize_kernel(StepState *st, const float *g_critic_tail, const
 
 // SampleTransitionsFromMemory (dqn.cpp:501-509): B uniform draws with replacement in [0,size)
 __global__ void sample_kernel(const StepState *st, unsigned long long seed, int B, int32_t *idx) {
+  DQNB_PDL_PROLOGUE();
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= B) return;
   const int size = st->ring_size;
@@ -78,6 +89,7 @@ struct GatherArgs {
 };
 
 __global__ void __launch_bounds__(128) gather_kernel(const GatherArgs a) {
+  DQNB_PDL_PROLOGUE();
   const int n = blockIdx.x;
   const bool valid = n < a.B;
   long long phys = 0;
@@ -143,6 +155,7 @@ struct HeadArgs {
 };
 
 __global__ void __launch_bounds__(256) head_fwd_kernel(const HeadArgs a) {
+  DQNB_PDL_PROLOGUE();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = blockIdx.x * 8 + warp;
   if (n >= a.rows) return;
@@ -191,6 +204,7 @@ struct QArgs {
 };
 
 __global__ void __launch_bounds__(256) q_kernel(const QArgs a) {
+  DQNB_PDL_PROLOGUE();
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   double contrib = 0.0;
   if (n < a.B) {
@@ -233,6 +247,7 @@ struct HeadBwdXArgs {
   float *dZ; long long dz_plane; int rows_pad;
 };
 __global__ void __launch_bounds__(256) head_bwd_x_kernel(const HeadBwdXArgs a) {
+  DQNB_PDL_PROLOGUE();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)a.rows_pad * a.Kp) return;
   const int n = (int)(i / a.Kp), k = (int)(i % a.Kp);
@@ -257,6 +272,7 @@ struct HeadBwdWArgs {
   float *gpart; long long gpart_stride; long long hw_off, hb_off;
 };
 __global__ void __launch_bounds__(512) head_bwd_w_kernel(const HeadBwdWArgs a) {
+  DQNB_PDL_PROLOGUE();
   __shared__ float red[4][kActorOut][128];
   const int k = blockIdx.x * 128 + (threadIdx.x & 127), sub = threadIdx.x >> 7, split = blockIdx.y;
   const int per = a.rows_pad / kGradSplits;
@@ -296,6 +312,7 @@ struct ColsumArgs {
   float *gpart; long long gpart_stride;
 };
 __global__ void __launch_bounds__(512) colsum_kernel(const ColsumArgs a) {
+  DQNB_PDL_PROLOGUE();
   __shared__ float red[4][128];
   int l = 0;
   while (l + 1 < a.n_layers && (int)blockIdx.x >= a.blk_begin[l + 1]) ++l;
@@ -325,6 +342,7 @@ struct InvertArgs {
   float *tap_raw, *tap_inv;    // [Bp][10] debug taps
 };
 __global__ void __launch_bounds__(256) invert_kernel(const InvertArgs a) {
+  DQNB_PDL_PROLOGUE();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.Bp * 16) return;
   const int n = i >> 4, h = i & 15;
@@ -361,6 +379,7 @@ struct ReduceArgs {
   int do_reduce, do_sumsq;
 };
 __global__ void __launch_bounds__(256) reduce_kernel(const ReduceArgs a) {
+  DQNB_PDL_PROLOGUE();
   const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   float ss = 0.f;
   if (i < a.flat) {
@@ -411,6 +430,7 @@ struct AdamArgs {
   HyperParams hp;
 };
 __global__ void __launch_bounds__(256) adam_kernel(const AdamArgs a) {
+  DQNB_PDL_PROLOGUE();
   __shared__ float s_scale;
   __shared__ double red[8];
   {
@@ -477,17 +497,20 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamArgs a) {
 
 // split an fp32 array into (hi, lo) planes / join it back (parameter import / export)
 __global__ void split_kernel(const float *x, float *hi, float *lo, long long n) {
+  DQNB_PDL_PROLOGUE();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float h = tf32_hi(x[i]);
   hi[i] = h; lo[i] = x[i] - h;
 }
 __global__ void join_kernel(const float *hi, const float *lo, float *x, long long n) {
+  DQNB_PDL_PROLOGUE();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) x[i] = hi[i] + lo[i];
 }
 // standalone gemm test: sum split planes
 __global__ void sum_planes_kernel(const float *part, long long stride, int planes, float *out, long long n) {
+  DQNB_PDL_PROLOGUE();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float s = 0.f;

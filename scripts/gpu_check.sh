@@ -4,8 +4,7 @@
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.txt 2>&1
 nproc > gpurun_out/nproc.txt
-echo "== perf gemm2"; timeout 120 python scripts/perf_gemm2.py 2>&1 | tee gpurun_out/perf_gemm2.log
 echo "== gemm"; timeout 300 python -m pytest tests/test_gpu_gemm.py -q -m gpu 2>&1 | tail -25 | tee gpurun_out/t_gemm.log
 echo "== update"; timeout 1200 python -m pytest tests/test_gpu_update.py -q -m gpu 2>&1 | tail -60 | tee gpurun_out/t_update.log
 echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5 | tee gpurun_out/smoke.log
-echo "== bench"; timeout 900 python bench.py --steps 300 --warmup 20 2>&1 | tail -5 | tee gpurun_out/bench.log
+echo "== bench"; timeout 900 python bench.py --steps 500 --warmup 20 2>&1 | tail -5 | tee gpurun_out/bench.log
