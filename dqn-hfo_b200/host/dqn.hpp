@@ -1,0 +1,131 @@
+// dqn.hpp — host-side mirror of the reference's learner class (reference src/dqn.hpp:16-244): same
+// namespace, type aliases, member names and argument meaning, so dqn_main-style callers compile
+// against it unchanged.  Where the reference owns four caffe::Net and two caffe::Solver objects,
+// this class owns one opaque dqnb_handle (include/dqn_b200.h): replay memory, weights, Adam state
+// and target nets live in HBM and every FLOP runs in libdqn_b200.so.
+//
+// Differences forced by the environment (no Boost/Caffe/glog/gflags in the image):
+//   boost::optional -> std::optional; caffe::SolverParameter/NetParameter -> shim/caffe_types.hpp;
+//   kMinibatchSize stays the reference's compile-time default but the minibatch actually used is
+//   the run-time flag -batch_size (BASELINE configs need 1024/4096/8192).
+#ifndef DQN_HPP_
+#define DQN_HPP_
+
+#include <HFO.hpp>
+#include <array>
+#include <deque>
+#include <memory>
+#include <mutex>
+#include <optional>
+#include <random>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "hfo_game.hpp"
+#include "shim/caffe_types.hpp"
+
+struct dqnb_handle_s;
+
+namespace dqn {
+
+constexpr auto kStateInputCount = 1;       // dqn.hpp:18
+constexpr auto kMinibatchSize = 32;        // dqn.hpp:19 (default of -batch_size)
+constexpr auto kActionSize = 4;            // dqn.hpp:20
+constexpr auto kActionParamSize = 6;       // dqn.hpp:21
+
+using ActorOutput = std::array<float, kActionSize + kActionParamSize>;
+using StateData = std::vector<float>;
+using StateDataSp = std::shared_ptr<StateData>;
+using InputStates = std::array<StateDataSp, kStateInputCount>;
+using Transition = std::tuple<InputStates, ActorOutput, float, float, std::optional<StateDataSp>>;
+
+class DQN {
+ public:
+  DQN(caffe::SolverParameter &actor_solver_param, caffe::SolverParameter &critic_solver_param,
+      std::string save_path, int state_size, int tid);
+  ~DQN();
+
+  // Benchmark the speed of updates (dqn.cpp:487-498)
+  void Benchmark(int iterations = 1000);
+
+  // Loading methods (dqn.cpp:525-557, :1180-1226)
+  void RestoreActorSolver(const std::string &actor_solver);
+  void RestoreCriticSolver(const std::string &critic_solver);
+  void LoadActorWeights(const std::string &actor_model_file);
+  void LoadCriticWeights(const std::string &critic_weights);
+  void LoadReplayMemory(const std::string &filename);
+
+  // Snapshot the model/solver/replay memory (dqn.cpp:582-620)
+  void Snapshot();
+  void Snapshot(const std::string &snapshot_prefix, bool remove_old = false, bool snapshot_memory = true);
+
+  ActorOutput GetRandomActorOutput();                                   // dqn.cpp:664-682
+  ActorOutput SelectAction(const InputStates &input_states, double epsilon);   // dqn.cpp:684-686
+  std::vector<ActorOutput> SelectActions(const std::vector<InputStates> &states_batch, double epsilon);  // :695-711
+  Action SampleAction(const ActorOutput &actor_output);                 // dqn.cpp:180-194
+  float EvaluateAction(const InputStates &input_states, const ActorOutput &action);  // dqn.cpp:688-693
+
+  void AddTransition(const Transition &transition);                     // dqn.cpp:768-773
+  void AddTransitions(const std::vector<Transition> &transitions);      // dqn.cpp:775-781
+  void LabelTransitions(std::vector<Transition> &transitions);          // dqn.cpp:783-797
+  void Update();                                                        // dqn.cpp:799-826
+
+  void ClearReplayMemory();
+  void SnapshotReplayMemory(const std::string &filename);               // dqn.cpp:1146-1178
+  int memory_size() const;
+
+  // Multi-agent sharing (dqn.cpp:1037-1083) is outside the hot-path scope.
+  void ShareParameters(DQN &other, int num_actor_layers_to_share, int num_critic_layers_to_share);
+  void ShareReplayMemory(DQN &other);
+
+  int min_iter() const { return std::min(actor_iter(), critic_iter()); }
+  int max_iter() const { return std::max(actor_iter(), critic_iter()); }
+  int critic_iter() const;
+  int actor_iter() const;
+  int state_size() const { return state_size_; }
+  const std::string &save_path() const { return save_path_; }
+  int unum() const { return unum_; }
+  void set_unum(int unum) { unum_ = unum; }
+
+  // Not in the reference: what the last Update() returned (dqn.cpp:971) and the raw handle.
+  std::pair<float, float> last_update() const { return last_update_; }
+  dqnb_handle_s *handle() { return h_; }
+
+ protected:
+  std::pair<float, float> UpdateActorCritic();                          // dqn.cpp:828-972
+  std::vector<int> SampleTransitionsFromMemory(int n);                  // dqn.cpp:501-509
+  void refresh_iters() const;
+
+  caffe::SolverParameter actor_solver_param_, critic_solver_param_;
+  const int replay_memory_capacity_;
+  const double gamma_;
+  dqnb_handle_s *h_;
+  std::mt19937 random_engine;
+  float smoothed_critic_loss_, smoothed_actor_loss_;
+  int last_snapshot_iter_;
+  std::string save_path_;
+  const int state_size_;
+  int batch_size_;
+  int tid_;
+  int unum_;
+  mutable int actor_iter_cache_, critic_iter_cache_;
+  mutable bool iters_dirty_;
+  std::pair<float, float> last_update_;
+};
+
+caffe::NetParameter CreateActorNet(int state_size);    // dqn.cpp:418-429
+caffe::NetParameter CreateCriticNet(int state_size);   // dqn.cpp:431-454
+
+Action GetAction(const ActorOutput &actor_output);     // dqn.cpp:196-208
+std::vector<std::string> FilesMatchingRegexp(const std::string &regexp);   // dqn.cpp:559-580
+void RemoveFilesMatchingRegexp(const std::string &regexp);
+void RemoveSnapshots(const std::string &regexp, int min_iter);
+void FindLatestSnapshot(const std::string &snapshot_prefix, std::string &actor_snapshot,
+                        std::string &critic_snapshot, std::string &memory_snapshot);
+int FindHiScore(const std::string &snapshot_prefix);
+std::string PrintActorOutput(const ActorOutput &actor_output);
+
+}  // namespace dqn
+
+#endif /* DQN_HPP_ */

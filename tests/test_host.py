@@ -1,0 +1,79 @@
+"""The C++ host mirror (dqn-hfo_b200/host): builds with g++, its CPU self-test passes, and on the
+GPU the dqn_main look-alike trains, logs the reference's log lines, snapshots and resumes."""
+import glob
+import os
+import re
+import subprocess
+
+import pytest
+
+from util import ROOT, pkg
+
+HOST = os.path.join(ROOT, "dqn-hfo_b200", "host")
+
+
+def build_host():
+    pkg()  # makes sure libdqn_b200.so exists
+    subprocess.run(["make", "-C", HOST], check=True, stdout=subprocess.DEVNULL)
+
+
+def test_host_mirror_builds_and_cpu_selftest_passes():
+    build_host()
+    out = subprocess.run([os.path.join(HOST, "host_selftest")], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "host_selftest: ok" in out.stdout
+
+
+def test_host_headers_keep_the_reference_api_surface():
+    """Every public member / free function of the reference's dqn.hpp:56-242 and hfo_game.hpp:7-60 that
+    is in scope must exist under the same name in the mirror headers."""
+    dqn_hpp = open(os.path.join(HOST, "dqn.hpp")).read()
+    for name in ["Benchmark", "RestoreActorSolver", "RestoreCriticSolver", "LoadActorWeights", "LoadCriticWeights",
+                 "LoadReplayMemory", "Snapshot", "GetRandomActorOutput", "SelectAction", "SelectActions", "SampleAction",
+                 "EvaluateAction", "AddTransition", "AddTransitions", "LabelTransitions", "Update", "ClearReplayMemory",
+                 "SnapshotReplayMemory", "memory_size", "ShareParameters", "ShareReplayMemory", "min_iter", "max_iter",
+                 "critic_iter", "actor_iter", "state_size", "save_path", "unum", "set_unum", "CreateActorNet",
+                 "CreateCriticNet", "GetAction", "FilesMatchingRegexp", "RemoveFilesMatchingRegexp", "RemoveSnapshots",
+                 "FindLatestSnapshot", "FindHiScore", "PrintActorOutput", "kStateInputCount", "kMinibatchSize",
+                 "kActionSize", "kActionParamSize", "ActorOutput", "StateDataSp", "InputStates", "Transition"]:
+        assert re.search(r"\b%s\b" % name, dqn_hpp), name
+    game_hpp = open(os.path.join(HOST, "hfo_game.hpp")).read()
+    for name in ["struct Action", "NumStateFeatures", "kPassVelThreshold", "StartHFOServer", "StartDummyTeammate",
+                 "StartDummyGoalie", "StartChaser", "StopHFOServer", "ConnectToServer", "GetRandomHFOAction",
+                 "class HFOGameState", "move_to_ball_reward", "kick_to_goal_reward", "EOT_reward", "pass_reward"]:
+        assert name in game_hpp, name
+
+
+@pytest.mark.gpu
+def test_dqn_main_benchmark_train_snapshot_resume(tmp_path):
+    build_host()
+    exe = os.path.join(HOST, "dqn")
+    # -benchmark (dqn_main.cpp:332-338 -> DQN::Benchmark dqn.cpp:487-498)
+    out = subprocess.run([exe, "-benchmark", "-batch_size=1024", "-benchmark_iters=100", "-memory=20000", "-seed=3",
+                          "-frames_per_trial=2000"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    m = re.search(r"Average Update: ([0-9.eE+-]+) ms", out.stderr)
+    assert m and 0 < float(m.group(1)) < 50, out.stderr[-2000:]
+    # short training run: episodes, updates, loss lines, final snapshot
+    prefix = str(tmp_path / "run")
+    args = [exe, f"-save={prefix}", "-max_iter=120", "-memory_threshold=64", "-memory=5000", "-explore=50", "-seed=5",
+            "-loss_display_iter=50", "-update_ratio=1.0", "-frames_per_trial=60", "-evaluate_freq=100000",
+            "-snapshot_freq=100000", "-hidden=128,64,64,32"]
+    out = subprocess.run(args, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-3000:]
+    log = out.stderr
+    assert re.search(r"\[Agent0\] Episode \d+ reward = ", log)                       # dqn_main.cpp:355-356
+    assert re.search(r"\[Agent0\] Critic Iteration \d+, loss = ", log)               # dqn.cpp:807-808
+    assert re.search(r"\[Agent0\] Actor Iteration \d+, avg_q_value = ", log)         # dqn.cpp:813-814
+    snaps = sorted(os.path.basename(p) for p in glob.glob(prefix + "_agent0_*"))
+    assert any(s.endswith(".solverstate") and "_actor_iter_" in s for s in snaps), snaps
+    assert any(s.endswith(".caffemodel") and "_critic_iter_" in s for s in snaps), snaps
+    assert any(s.endswith(".replaymemory") for s in snaps), snaps
+    # resume: picks up the newest snapshot and continues past its iteration (dqn_main.cpp:213-220,:268-286)
+    args2 = [a if not a.startswith("-max_iter") else "-max_iter=160" for a in args]
+    out2 = subprocess.run(args2, capture_output=True, text=True, timeout=600)
+    assert out2.returncode == 0, out2.stderr[-3000:]
+    assert "Actor solver state resuming from" in out2.stderr and "Loading replay memory from" in out2.stderr
+    its = [int(re.search(r"_actor_iter_(\d+)\.solverstate", s).group(1)) for s in
+           (os.path.basename(p) for p in glob.glob(prefix + "_agent0_actor_iter_*.solverstate"))]
+    assert max(its) >= 160
