@@ -5,6 +5,7 @@
 #include "../../include/dqn_b200.h"
 
 #include <dlfcn.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -209,12 +210,16 @@ struct SplitMat {           // [2][rows][ld] fp32 in HBM
 };
 
 struct Op {                 // one kernel launch of the update / act sequence
-  enum Kind { GEMM, GATHER, SAMPLE, HEAD_FWD, QK, HEAD_BWD_X, HEAD_BWD_W, COLSUM, INVERT, REDUCE,
+  enum Kind { GEMM, GATHER, SAMPLE, HEAD_FWD, CRITIC_HEAD, ACTOR_HEAD_BWD, HEAD_BWD_W, COLSUM, REDUCE,
               ALLREDUCE, ADAM, PREP, FINALIZE, FORK, JOIN } kind;
   int branch = 0;           // 0 = main stream; 1, 2 = side streams between FORK and JOIN
+  int wait_ev = -1;         // event the op's stream waits for before the launch (cross-branch edge)
+  int rec_ev = -1;          // event recorded on the op's stream after the launch
+  int mask = 3;             // FORK / JOIN: which side streams take part
+  int variant = 0;          // 0: always; 1: only when indices are drawn on the device; 2: only when injected
   GemmArgs gemm; dim3 grid;
-  GatherArgs gather; HeadArgs head; QArgs q; HeadBwdXArgs hbx; HeadBwdWArgs hbw; ColsumArgs cs;
-  InvertArgs inv; ReduceArgs red; AdamArgs adam;
+  GatherArgs gather; HeadArgs head; CriticHeadArgs ch; ActorHeadBwdArgs ahb; HeadBwdWArgs hbw; ColsumArgs cs;
+  ReduceArgs red; AdamArgs adam;
   float *ar_buf = nullptr; size_t ar_count = 0;
   int blocks = 0;
 };
@@ -230,6 +235,7 @@ struct dqnb_handle_s {
   cudaStream_t stream = nullptr;
   cudaStream_t side[2] = {nullptr, nullptr};          // independent forward chains run beside the main one
   cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+  cudaEvent_t evs[8] = {};                            // cross-branch edges inside one update
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::vector<void *> allocs;
   std::vector<void *> pinned;
@@ -248,7 +254,7 @@ struct dqnb_handle_s {
   SplitMat Xs, Xsn, Xc, Xct, Xcp;
   float *reward = nullptr, *mc = nullptr, *term = nullptr, *y = nullptr;
   float *q_next = nullptr, *q = nullptr, *q_pi = nullptr;
-  float *q16 = nullptr, *q16c = nullptr, *a16_t = nullptr, *a16_pi = nullptr, *d16c = nullptr, *d16a = nullptr;
+  float *a16_t = nullptr, *a16_pi = nullptr, *d16c = nullptr, *d16a = nullptr;
   float *d_in = nullptr, *tap_raw = nullptr, *tap_inv = nullptr;
   SplitMat actAT[DQNB_MAX_HIDDEN], actCT[DQNB_MAX_HIDDEN], actC[DQNB_MAX_HIDDEN], actA[DQNB_MAX_HIDDEN], dZ[DQNB_MAX_HIDDEN];
   // act path
@@ -258,6 +264,7 @@ struct dqnb_handle_s {
   // step state / results
   StepState *st = nullptr;
   float *results = nullptr; int max_slots = 4096;
+  unsigned int *ticket = nullptr;
   float *h_results = nullptr;
   // staging for replay appends
   float *h_stage_s = nullptr, *h_stage_sn = nullptr, *h_stage_misc = nullptr; int stage_rows = 0;
@@ -267,6 +274,7 @@ struct dqnb_handle_s {
   int kernels_per_update_sampled = 0, kernels_per_update_injected = 0;
   int64_t launches = 0;
   void *comm = nullptr;
+  long long *trace = nullptr; int trace_ops = 0;   // DQNB_TRACE=1: per-GEMM timeline stamps (gemm.cuh DQNB_STAMP)
   HyperParams hp;
   SegTable segs[2];
 };
@@ -384,7 +392,7 @@ static void op_head_fwd(const NetGeom &g, const float *P, const SplitMat &H, int
   a.W = P + g.hw_off; a.w_plane = g.flat; a.bias = P + g.hb_off; a.b_plane = g.flat;
   a.J = g.head_real; a.rows = rows; a.out16 = out16;
   if (dst) { a.dst = dst->p; a.dst_plane = dst->plane(); a.ldd = dst->ld; a.dst_col = dst_col; }
-  op->blocks = (rows + 7) / 8;
+  op->blocks = (rows + kHeadRowsPerBlock - 1) / kHeadRowsPerBlock;
 }
 
 }  // namespace dqnb
@@ -421,11 +429,10 @@ static int launch_op(dqnb_handle_s *h, const Op &op, cudaStream_t s) {
                    (unsigned long long)h->cfg.seed, h->B, h->idx);
       break;
     case Op::HEAD_FWD: e = launch_k(head_fwd_kernel, dim3(op.blocks), dim3(256), 0, s, op.head); break;
-    case Op::QK: e = launch_k(q_kernel, dim3(op.blocks), dim3(256), 0, s, op.q); break;
-    case Op::HEAD_BWD_X: e = launch_k(head_bwd_x_kernel, dim3(op.blocks), dim3(256), 0, s, op.hbx); break;
-    case Op::HEAD_BWD_W: e = launch_k(head_bwd_w_kernel, op.grid, dim3(512), 0, s, op.hbw); break;
-    case Op::COLSUM: e = launch_k(colsum_kernel, op.grid, dim3(512), 0, s, op.cs); break;
-    case Op::INVERT: e = launch_k(invert_kernel, dim3(op.blocks), dim3(256), 0, s, op.inv); break;
+    case Op::CRITIC_HEAD: e = launch_k(critic_head_kernel, dim3(op.blocks), dim3(256), 0, s, op.ch); break;
+    case Op::ACTOR_HEAD_BWD: e = launch_k(actor_head_bwd_kernel, dim3(op.blocks), dim3(256), 0, s, op.ahb); break;
+    case Op::HEAD_BWD_W: e = launch_k(head_bwd_w_kernel, op.grid, dim3(1024), 0, s, op.hbw); break;
+    case Op::COLSUM: e = launch_k(colsum_kernel, op.grid, dim3(1024), 0, s, op.cs); break;
     case Op::REDUCE: e = launch_k(reduce_kernel, dim3(op.blocks), dim3(256), 0, s, op.red); break;
     case Op::ADAM: e = launch_k(adam_kernel, dim3(op.blocks), dim3(256), 0, s, op.adam); break;
     case Op::PREP: e = launch_k(prep_kernel, dim3(1), dim3(32), 0, s, h->st, h->hp); break;
@@ -450,20 +457,25 @@ static int launch_op(dqnb_handle_s *h, const Op &op, cudaStream_t s) {
 static int run_ops(dqnb_handle_s *h, const std::vector<Op> &ops, cudaStream_t s, bool skip_sample, int *count) {
   int n = 0;
   for (const Op &op : ops) {
-    if (skip_sample && op.kind == Op::SAMPLE) continue;
+    if (op.variant == (skip_sample ? 1 : 2)) continue;
     if (op.kind == Op::FORK) {          // side streams pick up after everything queued on the main one
       DQNB_CUDA(cudaEventRecord(h->ev_fork, s));
-      for (int b = 0; b < 2; ++b) DQNB_CUDA(cudaStreamWaitEvent(h->side[b], h->ev_fork, 0));
+      for (int b = 0; b < 2; ++b)
+        if (op.mask & (1 << b)) DQNB_CUDA(cudaStreamWaitEvent(h->side[b], h->ev_fork, 0));
       continue;
     }
     if (op.kind == Op::JOIN) {
-      for (int b = 0; b < 2; ++b) {
-        DQNB_CUDA(cudaEventRecord(h->ev_join[b], h->side[b]));
-        DQNB_CUDA(cudaStreamWaitEvent(s, h->ev_join[b], 0));
-      }
+      for (int b = 0; b < 2; ++b)
+        if (op.mask & (1 << b)) {
+          DQNB_CUDA(cudaEventRecord(h->ev_join[b], h->side[b]));
+          DQNB_CUDA(cudaStreamWaitEvent(s, h->ev_join[b], 0));
+        }
       continue;
     }
-    if (launch_op(h, op, op.branch ? h->side[op.branch - 1] : s)) return -1;
+    cudaStream_t os = op.branch ? h->side[op.branch - 1] : s;
+    if (op.wait_ev >= 0) DQNB_CUDA(cudaStreamWaitEvent(os, h->evs[op.wait_ev], 0));
+    if (launch_op(h, op, os)) return -1;
+    if (op.rec_ev >= 0) DQNB_CUDA(cudaEventRecord(h->evs[op.rec_ev], os));
     if (op.kind != Op::ALLREDUCE) ++n;
   }
   if (count) *count = n;
@@ -485,30 +497,44 @@ static int build_forward(dqnb_handle_s *h, const NetGeom &g, const float *P, con
   return 0;
 }
 
-// tower backward from dZ[top] (already masked): weight/bias gradient partials (optional) + dX chain
+// tower backward from dZ[top] (already masked by the head backward).  The dX chain is the critical
+// path and stays on the main stream; with want_dw the weight-gradient GEMMs, the head gradients and the
+// bias column sums run on side stream 1, each gated by an event on the dZ it consumes, and JOIN back
+// before the gradient reduction.
 static int build_backward(dqnb_handle_s *h, const NetGeom &g, const float *P, const SplitMat &X,
-                          SplitMat *acts, bool want_dw, SegTable *segs, std::vector<Op> &ops) {
+                          SplitMat *acts, bool want_dw, SegTable *segs, const Op *head_bwd_w,
+                          std::vector<Op> &ops) {
   const int top = g.n_hidden - 1;
+  if (g.n_hidden + 1 > 8) DQNB_FAIL("too many layers for the event table");
+  if (want_dw) {
+    Op f; f.kind = Op::FORK; f.mask = 1; ops.push_back(f);    // side 1 joins after head_bwd_x (dZ[top] ready)
+    if (head_bwd_w) { Op w = *head_bwd_w; w.branch = 1; ops.push_back(w); }
+  }
   for (int l = top; l >= 0; --l) {
-    if (l > 0) {
-      Op op;
-      if (op_dx(h->cfg, g, l, P, h->dZ[l], acts[l - 1], h->dZ[l - 1], &op)) return -1;
-      ops.push_back(op);
-    }
     if (want_dw) {
       Op op;
       int splits = 1;
       if (op_dw(h->cfg, g, l, h->dZ[l], l > 0 ? acts[l - 1] : X, h->Gpart[g.critic], h->gpart_stride[g.critic], &splits, &op)) return -1;
+      op.branch = 1;
+      if (l < top) op.wait_ev = l;                              // dZ[l] is produced by the dX op below
       ops.push_back(op);
       // segment table entries (internal flat order: W_l then b_l)
       SegTable &T = *segs;
       T.begin[2 * l] = g.L[l].w_off; T.end[2 * l] = g.L[l].b_off; T.nsplit[2 * l] = splits;
       T.begin[2 * l + 1] = g.L[l].b_off; T.end[2 * l + 1] = g.L[l].b_off + g.L[l].Np; T.nsplit[2 * l + 1] = kGradSplits;
     }
+    if (l > 0) {
+      Op op;
+      if (op_dx(h->cfg, g, l, P, h->dZ[l], acts[l - 1], h->dZ[l - 1], &op)) return -1;
+      if (want_dw) op.rec_ev = l - 1;                           // dZ[l-1] ready
+      ops.push_back(op);
+    }
   }
   if (want_dw) {
     Op op;
     op.kind = Op::COLSUM;
+    op.branch = 1;
+    op.wait_ev = 0;                                             // all dZ exist once dZ[0] does
     ColsumArgs &a = op.cs;
     memset(&a, 0, sizeof(a));
     a.n_layers = g.n_hidden; a.rows_pad = h->Bp;
@@ -520,11 +546,13 @@ static int build_backward(dqnb_handle_s *h, const NetGeom &g, const float *P, co
     a.blk_begin[g.n_hidden] = blk;
     a.gpart = h->Gpart[g.critic]; a.gpart_stride = h->gpart_stride[g.critic];
     op.grid = dim3(blk, kGradSplits);
+    if (g.n_hidden == 1) op.wait_ev = -1;
     ops.push_back(op);
     SegTable &T = *segs;
     const int hs = 2 * g.n_hidden;
     T.begin[hs] = g.hw_off; T.end[hs] = g.flat; T.nsplit[hs] = kGradSplits;   // head W, b (+ zero tail)
     T.n = hs + 1;
+    Op j; j.kind = Op::JOIN; j.mask = 1; ops.push_back(j);
   }
   return 0;
 }
@@ -563,38 +591,32 @@ static void build_solver(dqnb_handle_s *h, int is_critic, const SegTable &segs, 
   ops.push_back(ad);
 }
 
-static void push_q(dqnb_handle_s *h, int mode, const float *q16, float *q_tap, float *d16, std::vector<Op> &ops) {
+// critic head (+ TD target | loss + head backward | policy seed + head backward), one fused kernel
+static void push_critic_head(dqnb_handle_s *h, int mode, const float *P, const SplitMat &Htop, float *q_tap,
+                             std::vector<Op> &ops) {
+  const NetGeom &g = h->gC;
   Op op;
-  op.kind = Op::QK;
-  QArgs &a = op.q;
+  op.kind = Op::CRITIC_HEAD;
+  CriticHeadArgs &a = op.ch;
   memset(&a, 0, sizeof(a));
-  a.mode = mode; a.B = h->B; a.q16 = q16; a.reward = h->reward; a.mc = h->mc; a.term = h->term;
-  a.y = h->y; a.q_tap = q_tap; a.d16 = d16; a.part = h->scal_part; a.hp = h->hp;
-  op.blocks = (h->B + 255) / 256;
+  a.mode = mode; a.B = h->B; a.rows_pad = h->Bp;
+  a.H = Htop.p; a.h_plane = Htop.plane(); a.ldh = Htop.ld; a.Kp = g.Hp;
+  a.W = P + g.hw_off; a.w_plane = g.flat; a.bias = P + g.hb_off; a.b_plane = g.flat;
+  a.reward = h->reward; a.mc = h->mc; a.term = h->term; a.y = h->y; a.q_tap = q_tap; a.d16 = h->d16c;
+  a.dZ = h->dZ[g.n_hidden - 1].p; a.dz_plane = h->dZ[g.n_hidden - 1].plane();
+  a.part = h->scal_part; a.hp = h->hp;
+  op.blocks = (h->Bp + kHeadRowsPerBlock - 1) / kHeadRowsPerBlock;
   ops.push_back(op);
 }
-static void push_head_bwd(dqnb_handle_s *h, const NetGeom &g, const float *P, const float *d16,
-                          const SplitMat &Htop, bool want_dw, std::vector<Op> &ops) {
-  const int top = g.n_hidden - 1;
-  Op x;
-  x.kind = Op::HEAD_BWD_X;
-  HeadBwdXArgs &a = x.hbx;
-  memset(&a, 0, sizeof(a));
-  a.d16 = d16; a.J = g.head_real; a.W = P + g.hw_off; a.w_plane = g.flat; a.Kp = g.Hp;
-  a.H = Htop.p; a.h_plane = Htop.plane(); a.ldh = Htop.ld;
-  a.dZ = h->dZ[top].p; a.dz_plane = h->dZ[top].plane(); a.rows_pad = h->Bp;
-  x.blocks = (int)(((long long)h->Bp * g.Hp + 255) / 256);
-  ops.push_back(x);
-  if (want_dw) {
-    Op w;
-    w.kind = Op::HEAD_BWD_W;
-    HeadBwdWArgs &b = w.hbw;
-    memset(&b, 0, sizeof(b));
-    b.d16 = d16; b.J = g.head_real; b.H = Htop.p; b.h_plane = Htop.plane(); b.ldh = Htop.ld; b.Kp = g.Hp;
-    b.rows_pad = h->Bp; b.gpart = h->Gpart[g.critic]; b.gpart_stride = h->gpart_stride[g.critic]; b.hw_off = g.hw_off; b.hb_off = g.hb_off;
-    w.grid = dim3((g.Hp + 127) / 128, kGradSplits);
-    ops.push_back(w);
-  }
+static Op make_head_bwd_w(dqnb_handle_s *h, const NetGeom &g, const float *d16, const SplitMat &Htop) {
+  Op w;
+  w.kind = Op::HEAD_BWD_W;
+  HeadBwdWArgs &b = w.hbw;
+  memset(&b, 0, sizeof(b));
+  b.d16 = d16; b.J = g.head_real; b.H = Htop.p; b.h_plane = Htop.plane(); b.ldh = Htop.ld; b.Kp = g.Hp;
+  b.rows_pad = h->Bp; b.gpart = h->Gpart[g.critic]; b.gpart_stride = h->gpart_stride[g.critic]; b.hw_off = g.hw_off; b.hb_off = g.hb_off;
+  w.grid = dim3((g.Hp + 127) / 128, kGradSplits);
+  return w;
 }
 
 static int build_update_ops(dqnb_handle_s *h) {
@@ -604,18 +626,21 @@ static int build_update_ops(dqnb_handle_s *h) {
   float *PA = h->P[DQNB_ACTOR], *PC = h->P[DQNB_CRITIC], *PAT = h->P[DQNB_ACTOR_TARGET], *PCT = h->P[DQNB_CRITIC_TARGET];
   const int topA = gA.n_hidden - 1, topC = gC.n_hidden - 1;
   Op op;
-  op.kind = Op::PREP; ops.push_back(op);
-  op.kind = Op::SAMPLE; ops.push_back(op);                       // dqn.cpp:846
-  op.kind = Op::GATHER;                                          // dqn.cpp:859-887
-  {
+  // dqn.cpp:846-887: draw the minibatch (device sampler, or caller-injected indices) and gather it;
+  // the same launch refreshes the per-update Adam scalars
+  for (int variant = 1; variant <= 2; ++variant) {
+    op.kind = Op::GATHER;
+    op.variant = variant;
     GatherArgs &a = op.gather;
     memset(&a, 0, sizeof(a));
-    a.st = h->st; a.idx = h->idx; a.ring_s = h->ring_s; a.ring_sn = h->ring_sn; a.ring_misc = h->ring_misc;
+    a.st = h->st; a.idx = h->idx; a.sample = variant == 1; a.seed = h->cfg.seed; a.hp = h->hp;
+    a.ring_s = h->ring_s; a.ring_sn = h->ring_sn; a.ring_misc = h->ring_misc;
     a.cap = h->cfg.replay_capacity; a.B = h->B; a.Bp = h->Bp; a.S = h->S; a.Sp = h->Sp; a.Kc = h->Kc;
     a.Xs = h->Xs.p; a.Xsn = h->Xsn.p; a.Xc = h->Xc.p; a.Xct = h->Xct.p; a.Xcp = h->Xcp.p;
     a.reward = h->reward; a.mc = h->mc; a.term = h->term;
+    ops.push_back(op);
   }
-  ops.push_back(op);
+  op.variant = 0;
   // Three independent forward chains run side by side (separate streams -> parallel graph branches):
   //   main  : dqn.cpp:889-891 CriticForwardThroughActor(critic_target, actor_target, s') + TD target
   //   side 1: forward half of critic_solver_->Step(1) on (s, a, p)            (dqn.cpp:904)
@@ -624,7 +649,6 @@ static int build_update_ops(dqnb_handle_s *h) {
   {
     const size_t mark = ops.size();
     if (build_forward(h, gC, PC, h->Xc, h->actC, ops)) return -1;
-    op_head_fwd(gC, PC, h->actC[topC], h->B, h->q16c, nullptr, 0, &op); ops.push_back(op);
     for (size_t i = mark; i < ops.size(); ++i) ops[i].branch = 1;
   }
   {
@@ -637,37 +661,41 @@ static int build_update_ops(dqnb_handle_s *h) {
   if (build_forward(h, gA, PAT, h->Xsn, h->actAT, ops)) return -1;
   op_head_fwd(gA, PAT, h->actAT[topA], h->B, h->a16_t, &h->Xct, h->S, &op); ops.push_back(op);
   if (build_forward(h, gC, PCT, h->Xct, h->actCT, ops)) return -1;
-  op_head_fwd(gC, PCT, h->actCT[topC], h->B, h->q16, nullptr, 0, &op); ops.push_back(op);
-  push_q(h, QMODE_TARGET, h->q16, h->q_next, nullptr, ops);      // dqn.cpp:892-900
+  push_critic_head(h, QMODE_TARGET, PCT, h->actCT[topC], h->q_next, ops);   // dqn.cpp:892-900
   op.kind = Op::JOIN; ops.push_back(op);
   // rest of critic_solver_->Step(1): loss, backward, clip, Adam (+ soft update of the target critic)
-  push_q(h, QMODE_LOSS, h->q16c, h->q, h->d16c, ops);
-  push_head_bwd(h, gC, PC, h->d16c, h->actC[topC], true, ops);
-  if (build_backward(h, gC, PC, h->Xc, h->actC, true, &h->segs[1], ops)) return -1;
+  push_critic_head(h, QMODE_LOSS, PC, h->actC[topC], h->q, ops);
+  Op hbw = make_head_bwd_w(h, gC, h->d16c, h->actC[topC]);
+  if (build_backward(h, gC, PC, h->Xc, h->actC, true, &h->segs[1], &hbw, ops)) return -1;
   build_solver(h, 1, h->segs[1], 0.5f * h->hp.inv_batch_global, ops);
   // dqn.cpp:913-916 critic forward on (s, a_pi) with the updated critic
   if (build_forward(h, gC, PC, h->Xcp, h->actC, ops)) return -1;
-  op_head_fwd(gC, PC, h->actC[topC], h->B, h->q16, nullptr, 0, &op); ops.push_back(op);
-  push_q(h, QMODE_POLICY, h->q16, h->q_pi, h->d16c, ops);        // dqn.cpp:918-921
+  push_critic_head(h, QMODE_POLICY, PC, h->actC[topC], h->q_pi, ops);       // dqn.cpp:918-921
   // dqn.cpp:923 critic.BackwardFrom(q_values_layer): only the input diff is consumed
-  push_head_bwd(h, gC, PC, h->d16c, h->actC[topC], false, ops);
-  if (build_backward(h, gC, PC, h->Xcp, h->actC, false, nullptr, ops)) return -1;
+  if (build_backward(h, gC, PC, h->Xcp, h->actC, false, nullptr, nullptr, ops)) return -1;
   if (op_dx_plain(h->cfg, gC, PC, h->dZ[0], h->d_in, &op)) return -1;
   ops.push_back(op);
-  op.kind = Op::INVERT;                                          // dqn.cpp:927-957
+  op.kind = Op::ACTOR_HEAD_BWD;                                  // dqn.cpp:927-961 inverting gradients + ShareDiff
   {
-    InvertArgs &a = op.inv;
+    ActorHeadBwdArgs &a = op.ahb;
     memset(&a, 0, sizeof(a));
-    a.B = h->B; a.Bp = h->Bp; a.S = h->S; a.ldin = h->Kc; a.d_in = h->d_in; a.a16 = h->a16_pi; a.d16 = h->d16a;
+    a.B = h->B; a.rows_pad = h->Bp; a.S = h->S; a.ldin = h->Kc; a.d_in = h->d_in; a.a16 = h->a16_pi; a.d16 = h->d16a;
     a.tap_raw = h->tap_raw; a.tap_inv = h->tap_inv;
-    op.blocks = (h->Bp * 16 + 255) / 256;
+    a.W = PA + gA.hw_off; a.w_plane = gA.flat; a.Kp = gA.Hp;
+    a.H = h->actA[topA].p; a.h_plane = h->actA[topA].plane(); a.ldh = h->actA[topA].ld;
+    a.dZ = h->dZ[topA].p; a.dz_plane = h->dZ[topA].plane();
+    op.blocks = (h->Bp + kHeadRowsPerBlock - 1) / kHeadRowsPerBlock;
   }
   ops.push_back(op);
-  // dqn.cpp:960-965 actor backward + ApplyUpdate
-  push_head_bwd(h, gA, PA, h->d16a, h->actA[topA], true, ops);
-  if (build_backward(h, gA, PA, h->Xs, h->actA, true, &h->segs[0], ops)) return -1;
+  // dqn.cpp:963-965 actor backward + ApplyUpdate
+  hbw = make_head_bwd_w(h, gA, h->d16a, h->actA[topA]);
+  if (build_backward(h, gA, PA, h->Xs, h->actA, true, &h->segs[0], &hbw, ops)) return -1;
   build_solver(h, 0, h->segs[0], h->hp.inv_batch_global, ops);
-  op.kind = Op::FINALIZE; ops.push_back(op);
+  {   // the last optimiser launch also publishes (critic_loss, avg_q) and advances the counters
+    AdamArgs &d = ops.back().adam;
+    d.finalize = 1; d.ticket = h->ticket; d.g_critic_tail = h->G[1] + gC.flat; d.g_actor_tail = h->G[0] + gA.flat;
+    d.results = h->results; d.max_slots = h->max_slots;
+  }
   return 0;
 }
 
@@ -723,6 +751,7 @@ int dqnb_destroy(dqnb_handle h) {
     if (h->side[b]) cudaStreamDestroy(h->side[b]);
   }
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  for (int i = 0; i < 8; ++i) if (h->evs[i]) cudaEventDestroy(h->evs[i]);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -736,6 +765,7 @@ static int create_impl(const dqnb_config *cfg, dqnb_handle_s *h) {
   if (c.struct_size != (int32_t)sizeof(dqnb_config)) DQNB_FAIL("dqnb_config.struct_size mismatch (%d vs %d)", c.struct_size, (int)sizeof(dqnb_config));
   if (c.state_size <= 0 || c.batch <= 0 || c.n_hidden < 1 || c.n_hidden > DQNB_MAX_HIDDEN) DQNB_FAIL("bad dimensions");
   for (int l = 0; l < c.n_hidden; ++l) if (c.hidden[l] <= 0) DQNB_FAIL("bad hidden size");
+  if (round_up(c.hidden[c.n_hidden - 1], 64) > kHeadMaxK) DQNB_FAIL("top tower layer wider than %d is not supported by the head kernels", kHeadMaxK);
   if (c.replay_capacity < 2) DQNB_FAIL("replay_capacity must be >= 2");
   if (c.world_size < 1 || c.rank < 0 || c.rank >= c.world_size) DQNB_FAIL("bad world_size/rank");
   int ndev = 0;
@@ -754,6 +784,7 @@ static int create_impl(const dqnb_config *cfg, dqnb_handle_s *h) {
     DQNB_CUDA(cudaEventCreateWithFlags(&h->ev_join[b], cudaEventDisableTiming));
   }
   DQNB_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+  for (int i = 0; i < 8; ++i) DQNB_CUDA(cudaEventCreateWithFlags(&h->evs[i], cudaEventDisableTiming));
   DQNB_CUDA(tc_prepare_all());
 
   h->S = c.state_size; h->Sp = round_up(c.state_size, 64); h->Kc = round_up(c.state_size + kActorOut, 64);
@@ -773,7 +804,7 @@ static int create_impl(const dqnb_config *cfg, dqnb_handle_s *h) {
   h->gpart_stride[0] = fA; h->gpart_stride[1] = fC;
   if (dalloc(h, &h->Gpart[0], (size_t)kGradSplits * fA) || dalloc(h, &h->Gpart[1], (size_t)kGradSplits * fC)) return -1;
   if (dalloc(h, &h->norm_part, (size_t)(fmax / 1024))) return -1;
-  h->n_scal = (h->B + 255) / 256;
+  h->n_scal = (h->Bp + kHeadRowsPerBlock - 1) / kHeadRowsPerBlock;     // one loss / avg-q partial per critic_head block
   if (dalloc(h, &h->scal_part, (size_t)h->n_scal)) return -1;
   // replay ring (rows padded to Sp floats = 256 B multiples: aligned, vectorisable gathers)
   const size_t cap = (size_t)c.replay_capacity;
@@ -784,7 +815,7 @@ static int create_impl(const dqnb_config *cfg, dqnb_handle_s *h) {
   float **vecs[] = {&h->reward, &h->mc, &h->term, &h->y, &h->q_next, &h->q, &h->q_pi};
   for (float **v : vecs) if (dalloc(h, v, (size_t)h->Bp)) return -1;
   const int rows16 = std::max(h->Bp, h->An);
-  float **m16[] = {&h->q16, &h->q16c, &h->a16_t, &h->a16_pi, &h->d16c, &h->d16a, &h->out16_act};
+  float **m16[] = {&h->a16_t, &h->a16_pi, &h->d16c, &h->d16a, &h->out16_act};
   for (float **v : m16) if (dalloc(h, v, (size_t)rows16 * 16)) return -1;
   if (dalloc(h, &h->d_in, (size_t)h->Bp * h->Kc) || dalloc(h, &h->tap_raw, (size_t)h->Bp * kActorOut) || dalloc(h, &h->tap_inv, (size_t)h->Bp * kActorOut)) return -1;
   for (int l = 0; l < c.n_hidden; ++l) {
@@ -794,12 +825,18 @@ static int create_impl(const dqnb_config *cfg, dqnb_handle_s *h) {
   }
   if (alloc_mat(h, &h->Xact, h->An, h->Sp) || alloc_mat(h, &h->Xeval, h->An, h->Kc)) return -1;
   if (halloc(h, &h->h_act_in, (size_t)2 * h->An * h->Kc) || halloc(h, &h->h_act_out, (size_t)h->An * 16)) return -1;
-  if (dalloc(h, &h->st, 1) || dalloc(h, &h->results, (size_t)2 * h->max_slots)) return -1;
+  if (dalloc(h, &h->st, 1) || dalloc(h, &h->results, (size_t)2 * h->max_slots) || dalloc(h, &h->ticket, 1)) return -1;
   if (halloc(h, &h->h_results, (size_t)2 * h->max_slots)) return -1;
   h->stage_rows = 4096;
   if (halloc(h, &h->h_stage_s, (size_t)h->stage_rows * h->Sp) || halloc(h, &h->h_stage_sn, (size_t)h->stage_rows * h->Sp) ||
       halloc(h, &h->h_stage_misc, (size_t)h->stage_rows * kMiscStride)) return -1;
   if (build_update_ops(h) || build_act_ops(h)) return -1;
+  if (getenv("DQNB_TRACE")) {
+    h->trace_ops = (int)h->update_ops.size();
+    if (dalloc(h, &h->trace, (size_t)8 * h->trace_ops)) return -1;
+    for (int i = 0; i < h->trace_ops; ++i)
+      if (h->update_ops[i].kind == Op::GEMM) h->update_ops[i].gemm.p.dbg_clk = h->trace + 8 * i;
+  }
   DQNB_CUDA(cudaStreamSynchronize(h->stream));
   DQNB_CUDA(cudaDeviceSynchronize());
   return 0;
@@ -1257,6 +1294,23 @@ int dqnb_sync(dqnb_handle h) {
 
 int64_t dqnb_kernel_launches(dqnb_handle h) { return h ? h->launches : -1; }
 
+// DQNB_TRACE=1 only: per-op timeline of the last update, 8 int64 per op of the update sequence
+// ({kind, branch} in slots 7/6 are filled here; slots 0-5 are globaltimer ns stamps of GEMM ops).
+int64_t dqnb_debug_trace(dqnb_handle h, long long *out, int64_t capacity) {
+  if (!h || !h->trace || !out) return -1;
+  const int64_t n = (int64_t)8 * h->trace_ops;
+  if (capacity < n) return -1;
+  cudaSetDevice(h->cfg.device);
+  cudaStreamSynchronize(h->stream);
+  if (cudaMemcpy(out, h->trace, sizeof(long long) * n, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  for (int i = 0; i < h->trace_ops; ++i) {
+    const Op &op = h->update_ops[i];
+    out[8 * i + 7] = (long long)op.kind * 1000 + op.branch;
+    if (op.kind == Op::GEMM) out[8 * i + 6] = ((long long)op.grid.x << 40) | ((long long)op.grid.y << 20) | op.grid.z | ((long long)(op.gemm.p.K / 32) << 52);
+  }
+  return n;
+}
+
 int64_t dqnb_debug_read(dqnb_handle h, const char *name, float *out, int64_t capacity) {
   if (!h || !name || !out) return -1;
   if (cudaSetDevice(h->cfg.device) != cudaSuccess) return -1;
@@ -1297,8 +1351,8 @@ int64_t dqnb_debug_read(dqnb_handle h, const char *name, float *out, int64_t cap
 }
 
 // ----------------------------------- kernel unit test ------------------------------------------
-static long long g_dbg_clk[3];
-void dqnb_gemm_test_clocks(long long *out3) { for (int i = 0; i < 3; ++i) out3[i] = g_dbg_clk[i]; }
+static long long g_dbg_clk[8 * 32];
+void dqnb_gemm_test_clocks(long long *out, int n) { for (int i = 0; i < n && i < 8 * 32; ++i) out[i] = g_dbg_clk[i]; }
 
 int dqnb_gemm_test(int device, int gemm_mode, int a_mn, int b_mn, int M, int N, int K, int splits,
                    const float *A, const float *B, float *C, float *elapsed_ms) {
@@ -1307,8 +1361,8 @@ int dqnb_gemm_test(int device, int gemm_mode, int a_mn, int b_mn, int M, int N, 
   DQNB_CUDA(tc_prepare_all());
   const size_t na = (size_t)M * K, nb = (size_t)N * K, nc = (size_t)M * N;
   long long *dclk = nullptr;
-  DQNB_CUDA(cudaMalloc(&dclk, 3 * sizeof(long long)));
-  DQNB_CUDA(cudaMemset(dclk, 0, 3 * sizeof(long long)));
+  DQNB_CUDA(cudaMalloc(&dclk, sizeof(g_dbg_clk)));
+  DQNB_CUDA(cudaMemset(dclk, 0, sizeof(g_dbg_clk)));
   float *dA, *dB, *dAs, *dBs, *dP, *dC;
   DQNB_CUDA(cudaMalloc(&dA, na * 4)); DQNB_CUDA(cudaMalloc(&dB, nb * 4));
   DQNB_CUDA(cudaMalloc(&dAs, 2 * na * 4)); DQNB_CUDA(cudaMalloc(&dBs, 2 * nb * 4));
@@ -1338,7 +1392,9 @@ int dqnb_gemm_test(int device, int gemm_mode, int a_mn, int b_mn, int M, int N, 
   const int reps = 20;
   for (int r = 0; r < 1 + reps; ++r) {
     if (r == 1) DQNB_CUDA(cudaEventRecord(e0, 0));
-    if (gemm_mode == DQNB_GEMM_TCGEN05_3XTF32) tc_kernel_for(a_mn, b_mn, p.bn)<<<op.grid, TC_THREADS, tc_smem_for(p.bn)>>>(op.gemm);
+    p.dbg_clk = dclk + 8 * r;            // per-launch timeline slot
+    if (gemm_mode == DQNB_GEMM_TCGEN05_3XTF32)
+      DQNB_CUDA(launch_k(tc_kernel_for(a_mn, b_mn, p.bn), op.grid, dim3(TC_THREADS), (size_t)tc_smem_for(p.bn), (cudaStream_t)0, op.gemm));
     else gemm_simt_kernel<<<op.grid, 256>>>(op.gemm.p);
   }
   DQNB_CUDA(cudaEventRecord(e1, 0));

@@ -79,8 +79,11 @@ __global__ void sample_kernel(const StepState *st, unsigned long long seed, int 
 // -------------------------------------------------------------------------------------------
 // Replay gather (dqn.cpp:859-887): one block per minibatch row, threads along the feature axis.
 struct GatherArgs {
-  const StepState *st;
-  const int32_t *idx;
+  StepState *st;
+  int32_t *idx;                // deque indices of the minibatch rows
+  int sample;                  // 1: draw idx on the device (SampleTransitionsFromMemory, dqn.cpp:501-509)
+  unsigned long long seed;
+  HyperParams hp;
   const float *ring_s, *ring_sn, *ring_misc;
   int cap, B, Bp, S, Sp, Kc;
   float *Xs, *Xsn;           // [2][Bp][Sp]   actor inputs: s, s'
@@ -92,10 +95,31 @@ __global__ void __launch_bounds__(128) gather_kernel(const GatherArgs a) {
   DQNB_PDL_PROLOGUE();
   const int n = blockIdx.x;
   const bool valid = n < a.B;
+  if (n == 0 && threadIdx.x == 32) {
+    // per-update scalars (formerly a kernel of their own).  AdamSolver::ComputeUpdateValue: t = iter+1,
+    // correction evaluated in double (std::pow(float,int) promotes); consumed much later by adam_kernel.
+    StepState *st = a.st;
+    const int tc = st->critic_iter + 1, ta = st->actor_iter + 1;
+    const double b1 = (double)a.hp.beta1, b2 = (double)a.hp.beta2;
+    const float cc = (float)(sqrt(1.0 - pow(b2, (double)tc)) / (1.0 - pow(b1, (double)tc)));
+    const float ca = (float)(sqrt(1.0 - pow(b2, (double)ta)) / (1.0 - pow(b1, (double)ta)));
+    st->step_critic = __fmul_rn(a.hp.critic_lr, cc);
+    st->step_actor = __fmul_rn(a.hp.actor_lr, ca);
+    const int mx = max(ta, tc);       // max_iter() after both solvers stepped (dqn.cpp:967)
+    st->do_soft = (a.hp.soft_update_freq > 0 && mx % a.hp.soft_update_freq == 0) ? 1 : 0;
+  }
   long long phys = 0;
   float misc_term = 1.f;
   if (valid) {
-    phys = ((long long)a.st->ring_head + a.idx[n]) % a.cap;
+    int id;
+    if (a.sample) {
+      const int size = a.st->ring_size;
+      id = size > 0 ? sample_index(a.seed, a.st->step, (uint32_t)n, (uint32_t)size) : 0;
+      if (threadIdx.x == 0) a.idx[n] = id;
+    } else {
+      id = a.idx[n];
+    }
+    phys = ((long long)a.st->ring_head + id) % a.cap;
     misc_term = a.ring_misc[phys * kMiscStride + 12];
   }
   const bool has_next = valid && misc_term == 0.f;
@@ -154,23 +178,46 @@ struct HeadArgs {
   float *dst; long long dst_plane; int ldd; int dst_col;  // also scatter split(out) into a critic input
 };
 
+constexpr int kHeadRowsPerBlock = 8;    // one warp per minibatch row
+constexpr int kHeadMaxK = 4096;
+
+// The per-row head kernels are latency-bound (a few KB per row): every lane issues all of its
+// float4 loads for a 128-wide K chunk before using any of them, so a row costs about one trip to L2.
+__device__ __forceinline__ float4 ld4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+__device__ __forceinline__ float4 add4(const float4 a, const float4 b) {
+  return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+}
+__device__ __forceinline__ float dot4(const float4 a, const float4 b, float acc) {
+  acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); return fmaf(a.w, b.w, acc);
+}
+__device__ __forceinline__ void store_split4(float *hi, float *lo, const float4 v) {
+  const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+  *reinterpret_cast<float4 *>(hi) = h;
+  *reinterpret_cast<float4 *>(lo) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+}
+__device__ __forceinline__ float4 relu_bwd4(const float4 v, const float4 y) {
+  return make_float4(v.x * (y.x > 0.f ? 1.f : kNegSlope), v.y * (y.y > 0.f ? 1.f : kNegSlope),
+                     v.z * (y.z > 0.f ? 1.f : kNegSlope), v.w * (y.w > 0.f ? 1.f : kNegSlope));
+}
+
 __global__ void __launch_bounds__(256) head_fwd_kernel(const HeadArgs a) {
   DQNB_PDL_PROLOGUE();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n = blockIdx.x * 8 + warp;
+  const int n = blockIdx.x * kHeadRowsPerBlock + warp;
   if (n >= a.rows) return;
   const float *hh = a.H + (long long)n * a.ldh;
   float acc[kActorOut];
 #pragma unroll
   for (int j = 0; j < kActorOut; ++j) acc[j] = 0.f;
-  for (int k = lane; k < a.Kp; k += 32) {
-    const float x = hh[k] + hh[k + a.h_plane];
+  for (int k = lane * 4; k < a.Kp; k += 128) {      // Kp is a multiple of 64: the tail chunk is half-used
+    const float4 x = add4(ld4(hh + k), ld4(hh + k + a.h_plane));
+    float4 w[kActorOut];
 #pragma unroll
     for (int j = 0; j < kActorOut; ++j)
-      if (j < a.J) {
-        const long long o = (long long)j * a.Kp + k;
-        acc[j] = fmaf(x, a.W[o] + a.W[o + a.w_plane], acc[j]);
-      }
+      if (j < a.J) w[j] = add4(ld4(a.W + (long long)j * a.Kp + k), ld4(a.W + (long long)j * a.Kp + k + a.w_plane));
+#pragma unroll
+    for (int j = 0; j < kActorOut; ++j)
+      if (j < a.J) acc[j] = dot4(x, w[j], acc[j]);
   }
 #pragma unroll
   for (int j = 0; j < kActorOut; ++j)
@@ -190,118 +237,183 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const HeadArgs a) {
   }
 }
 
-// TD target (dqn.cpp:892-900), Euclidean loss forward/backward, policy-pass seed (dqn.cpp:918-921)
+// Critic head, fused per minibatch row (one warp per row):
+//   q = h . w_q + b_q                                         (q_values_layer, dqn.cpp:450)
+//   TARGET: y = beta*mc + (1-beta)*(terminal ? r : r + gamma*q)   in double, dqn.cpp:892-900
+//   LOSS  : EuclideanLoss forward/backward: dq = (q - y)/N, loss partial sum (q-y)^2
+//   POLICY: dq = -1 (dqn.cpp:918-921), avg-q partial sum q
+//   LOSS/POLICY also write the head backward into the tower top, masked by that layer's ReLU':
+//   dZ[n][k] = dq * w_q[k] * relu'(h[n][k])
 enum { QMODE_TARGET = 0, QMODE_LOSS = 1, QMODE_POLICY = 2 };
-struct QArgs {
-  int mode, B;
-  const float *q16;            // critic head output [rows][16], column 0
+struct CriticHeadArgs {
+  int mode, B, rows_pad;
+  const float *H; long long h_plane; int ldh; int Kp;
+  const float *W; long long w_plane; const float *bias; long long b_plane;
   const float *reward, *mc, *term;
   float *y;                    // TARGET: out ; LOSS: in
   float *q_tap;                // TARGET: q_next ; LOSS: q ; POLICY: q_pi
-  float *d16;                  // LOSS: dq = (q-y)/N ; POLICY: -1
+  float *d16;                  // LOSS: dq for the head weight gradient (column 0 of [rows][16])
+  float *dZ; long long dz_plane;
   double *part;                // per-block partial: LOSS sum (q-y)^2 ; POLICY sum q
   HyperParams hp;
 };
-
-__global__ void __launch_bounds__(256) q_kernel(const QArgs a) {
+__global__ void __launch_bounds__(256) critic_head_kernel(const CriticHeadArgs a) {
   DQNB_PDL_PROLOGUE();
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ double red[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.x * kHeadRowsPerBlock + warp;
   double contrib = 0.0;
-  if (n < a.B) {
-    const float q = a.q16[(long long)n * 16];
-    if (a.mode == QMODE_TARGET) {
-      const bool terminal = a.term[n] != 0.f;
-      // float off = terminal ? r : r + gamma_*q' (double expr narrowed); float target = beta*on + (1-beta)*off
-      const float off = terminal ? a.reward[n] : (float)((double)a.reward[n] + a.hp.gamma * (double)q);
-      a.y[n] = (float)(a.hp.beta * (double)a.mc[n] + (1 - a.hp.beta) * (double)off);
-      a.q_tap[n] = terminal ? 0.f : q;
-    } else if (a.mode == QMODE_LOSS) {
-      const float diff = q - a.y[n];
-      a.d16[(long long)n * 16] = __fmul_rn(a.hp.inv_batch_global, diff);
-      a.q_tap[n] = q;
-      contrib = (double)diff * (double)diff;
-    } else {
-      a.d16[(long long)n * 16] = -1.0f;
-      a.q_tap[n] = q;
-      contrib = (double)q;
+  if (n < a.rows_pad) {
+    const float *hh = a.H + (long long)n * a.ldh;
+    float dq = 0.f;
+    if (n < a.B) {
+      float acc = 0.f;
+      for (int k = lane * 4; k < a.Kp; k += 128)
+        acc = dot4(add4(ld4(hh + k), ld4(hh + k + a.h_plane)), add4(ld4(a.W + k), ld4(a.W + k + a.w_plane)), acc);
+      const float q = warp_sum(acc) + (a.bias[0] + a.bias[a.b_plane]);
+      if (a.mode == QMODE_TARGET) {
+        if (lane == 0) {
+          const bool terminal = a.term[n] != 0.f;
+          // float off = terminal ? r : r + gamma_*q' (double expr narrowed); float target = beta*on + (1-beta)*off
+          const float off = terminal ? a.reward[n] : (float)((double)a.reward[n] + a.hp.gamma * (double)q);
+          a.y[n] = (float)(a.hp.beta * (double)a.mc[n] + (1 - a.hp.beta) * (double)off);
+          a.q_tap[n] = terminal ? 0.f : q;
+        }
+      } else if (a.mode == QMODE_LOSS) {
+        const float diff = q - a.y[n];
+        dq = __fmul_rn(a.hp.inv_batch_global, diff);
+        if (lane == 0) { a.d16[(long long)n * 16] = dq; a.q_tap[n] = q; contrib = (double)diff * (double)diff; }
+      } else {
+        dq = -1.0f;
+        if (lane == 0) { a.q_tap[n] = q; contrib = (double)q; }
+      }
+    }
+    if (a.mode != QMODE_TARGET) {
+      float *zh = a.dZ + (long long)n * a.ldh, *zl = zh + a.dz_plane;
+      for (int k = lane * 4; k < a.Kp; k += 128) {        // operands are L1 hits from the dot product above
+        const float4 y = add4(ld4(hh + k), ld4(hh + k + a.h_plane));
+        const float4 w = add4(ld4(a.W + k), ld4(a.W + k + a.w_plane));
+        store_split4(zh + k, zl + k, relu_bwd4(make_float4(dq * w.x, dq * w.y, dq * w.z, dq * w.w), y));
+      }
     }
   }
   if (a.mode == QMODE_TARGET) return;
-  __shared__ double red[8];
-  contrib = warp_sum_d(contrib);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = contrib;
+  if (lane == 0) red[warp] = contrib;
   __syncthreads();
   if (threadIdx.x == 0) {
     double s = 0.0;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
+    for (int w = 0; w < 8; ++w) s += red[w];
     a.part[blockIdx.x] = s;
   }
 }
 
-// Head backward w.r.t. the tower top + leaky mask of that layer:
-//   dZ[n][k] = (sum_j d16[n][j] * W[j][k]) * relu'(h[n][k])       (Split sums the two actor heads)
-struct HeadBwdXArgs {
-  const float *d16; int J;
+// Actor heads backward, fused per row: inverting gradients (dqn.cpp:927-957) on the critic's input
+// diff columns [S, S+10), then Split-sum of the two heads' bottom diffs and the ReLU' of the tower top:
+//   dZ[n][k] = (sum_j d10[n][j] * W[j][k]) * relu'(h[n][k])
+struct ActorHeadBwdArgs {
+  int B, rows_pad, S, ldin;
+  const float *d_in;           // [Bp][ldin] fp32: dL/d(critic input)
+  const float *a16;            // actor outputs [Bp][16]
+  float *d16;                  // out: top diffs of the actor heads [Bp][16] (for the head weight gradient)
+  float *tap_raw, *tap_inv;    // [Bp][10] debug taps
   const float *W; long long w_plane; int Kp;
   const float *H; long long h_plane; int ldh;
-  float *dZ; long long dz_plane; int rows_pad;
+  float *dZ; long long dz_plane;
 };
-__global__ void __launch_bounds__(256) head_bwd_x_kernel(const HeadBwdXArgs a) {
+__global__ void __launch_bounds__(256) actor_head_bwd_kernel(const ActorHeadBwdArgs a) {
   DQNB_PDL_PROLOGUE();
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long long)a.rows_pad * a.Kp) return;
-  const int n = (int)(i / a.Kp), k = (int)(i % a.Kp);
-  float acc = 0.f;
-  for (int j = 0; j < a.J; ++j) {
-    const long long o = (long long)j * a.Kp + k;
-    acc = fmaf(a.d16[(long long)n * 16 + j], a.W[o] + a.W[o + a.w_plane], acc);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.x * kHeadRowsPerBlock + warp;
+  if (n >= a.rows_pad) return;
+  float diff = 0.f;
+  if (n < a.B && lane < kActorOut) {
+    diff = a.d_in[(long long)n * a.ldin + a.S + lane];
+    a.tap_raw[n * kActorOut + lane] = diff;
+    const float output = a.a16[(long long)n * 16 + lane];
+    float mn, mx;
+    if (lane < kActionSize) { mn = -1.0f; mx = 1.0f; }
+    else if (lane == kActionSize + 0 || lane == kActionSize + 4) { mn = 0.f; mx = 100.f; }
+    else { mn = -180.f; mx = 180.f; }
+    if (diff < 0) diff *= (mx - output) / (mx - mn);
+    else if (diff > 0) diff *= (output - mn) / (mx - mn);
+    a.tap_inv[n * kActorOut + lane] = diff;
   }
-  const long long ho = (long long)n * a.ldh + k;
-  const float y = a.H[ho] + a.H[ho + a.h_plane];
-  const float v = acc * (y > 0.f ? 1.f : kNegSlope);
-  const float h = tf32_hi(v);
-  a.dZ[ho] = h; a.dZ[ho + a.dz_plane] = v - h;
+  if (lane < 16) a.d16[(long long)n * 16 + lane] = diff;
+  float d[kActorOut];
+#pragma unroll
+  for (int j = 0; j < kActorOut; ++j) d[j] = __shfl_sync(0xffffffffu, diff, j);
+  const float *hh = a.H + (long long)n * a.ldh;
+  float *zh = a.dZ + (long long)n * a.ldh, *zl = zh + a.dz_plane;
+  for (int k = lane * 4; k < a.Kp; k += 128) {
+    const float4 y = add4(ld4(hh + k), ld4(hh + k + a.h_plane));
+    float4 w[kActorOut];
+#pragma unroll
+    for (int j = 0; j < kActorOut; ++j)
+      w[j] = add4(ld4(a.W + (long long)j * a.Kp + k), ld4(a.W + (long long)j * a.Kp + k + a.w_plane));
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < kActorOut; ++j) {
+      acc.x = fmaf(d[j], w[j].x, acc.x); acc.y = fmaf(d[j], w[j].y, acc.y);
+      acc.z = fmaf(d[j], w[j].z, acc.z); acc.w = fmaf(d[j], w[j].w, acc.w);
+    }
+    store_split4(zh + k, zl + k, relu_bwd4(acc, y));
+  }
 }
 
 // Head weight/bias gradients: dW[j][k] = sum_n d16[n][j] h[n][k] ; db[j] = sum_n d16[n][j].
-// grid (Kp/128, kGradSplits); 512 threads = 4 row sub-groups x 128 columns.
+// grid (Kp/128, kGradSplits); 1024 threads = 8 row sub-groups x 128 columns; the split's d16 rows are
+// staged in shared memory once, the H loads are unrolled so several are in flight per thread.
+constexpr int kRedSub = 8;
 struct HeadBwdWArgs {
   const float *d16; int J;
   const float *H; long long h_plane; int ldh; int Kp;
   int rows_pad;
   float *gpart; long long gpart_stride; long long hw_off, hb_off;
 };
-__global__ void __launch_bounds__(512) head_bwd_w_kernel(const HeadBwdWArgs a) {
+__global__ void __launch_bounds__(1024) head_bwd_w_kernel(const HeadBwdWArgs a) {
   DQNB_PDL_PROLOGUE();
-  __shared__ float red[4][kActorOut][128];
-  const int k = blockIdx.x * 128 + (threadIdx.x & 127), sub = threadIdx.x >> 7, split = blockIdx.y;
-  const int per = a.rows_pad / kGradSplits;
-  const int r0 = split * per, r1 = r0 + per;
+  __shared__ float red[kRedSub][kActorOut][128];
+  __shared__ float sd[128 * 16];             // up to 128 rows of d16 per split
+  const int col = threadIdx.x & 127, sub = threadIdx.x >> 7, split = blockIdx.y;
+  const int k = blockIdx.x * 128 + col;
+  const int per = a.rows_pad / kGradSplits;  // rows of this split (multiple of 16)
+  const int r0 = split * per;
   float acc[kActorOut];
+  float bias_acc = 0.f;                      // thread (sub 0, col j < J): sum_n d16[n][j]
 #pragma unroll
   for (int j = 0; j < kActorOut; ++j) acc[j] = 0.f;
-  if (k < a.Kp)
-    for (int n = r0 + sub; n < r1; n += 4) {
-      const long long ho = (long long)n * a.ldh + k;
-      const float x = a.H[ho] + a.H[ho + a.h_plane];
+  for (int c0 = 0; c0 < per; c0 += 128) {    // chunks of <= 128 rows
+    const int rows = min(128, per - c0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < rows * 16; i += blockDim.x) sd[i] = a.d16[(long long)(r0 + c0) * 16 + i];
+    __syncthreads();
+    if (sub == 0 && col < a.J)
+      for (int n = 0; n < rows; ++n) bias_acc += sd[n * 16 + col];
+    if (k < a.Kp) {
+#pragma unroll 4
+      for (int n = sub; n < rows; n += kRedSub) {
+        const long long ho = (long long)(r0 + c0 + n) * a.ldh + k;
+        const float x = a.H[ho] + a.H[ho + a.h_plane];
 #pragma unroll
-      for (int j = 0; j < kActorOut; ++j)
-        if (j < a.J) acc[j] = fmaf(a.d16[(long long)n * 16 + j], x, acc[j]);
+        for (int j = 0; j < kActorOut; ++j)
+          if (j < a.J) acc[j] = fmaf(sd[n * 16 + j], x, acc[j]);
+      }
     }
+  }
 #pragma unroll
-  for (int j = 0; j < kActorOut; ++j) red[sub][j][threadIdx.x & 127] = acc[j];
+  for (int j = 0; j < kActorOut; ++j) red[sub][j][col] = acc[j];
   __syncthreads();
   float *g = a.gpart + (long long)split * a.gpart_stride;
-  if (sub == 0 && k < a.Kp)
-    for (int j = 0; j < a.J; ++j)
-      g[a.hw_off + (long long)j * a.Kp + k] =
-          (red[0][j][threadIdx.x] + red[1][j][threadIdx.x]) + (red[2][j][threadIdx.x] + red[3][j][threadIdx.x]);
-  if (blockIdx.x == 0 && sub == 1 && (threadIdx.x & 127) < a.J) {
-    const int j = threadIdx.x & 127;
-    float s = 0.f;
-    for (int n = r0; n < r1; ++n) s += a.d16[(long long)n * 16 + j];
-    g[a.hb_off + j] = s;
+  // 1024 threads finish the (J x 128) outputs: thread -> (j = sub.., col)
+  for (int j = sub; j < a.J; j += kRedSub) {
+    if (k < a.Kp) {
+      float s = 0.f;
+#pragma unroll
+      for (int t = 0; t < kRedSub; ++t) s += red[t][j][col];
+      g[a.hw_off + (long long)j * a.Kp + k] = s;
+    }
   }
+  if (blockIdx.x == 0 && sub == 0 && col < a.J) g[a.hb_off + col] = bias_acc;
 }
 
 // Bias gradients of the tower layers: db_l[c] = sum_n dZ_l[n][c] (Caffe: gemv(dY^T, ones)).
@@ -311,55 +423,33 @@ struct ColsumArgs {
   int blk_begin[9];            // prefix sums of Np/128 column blocks
   float *gpart; long long gpart_stride;
 };
-__global__ void __launch_bounds__(512) colsum_kernel(const ColsumArgs a) {
+__global__ void __launch_bounds__(1024) colsum_kernel(const ColsumArgs a) {
   DQNB_PDL_PROLOGUE();
-  __shared__ float red[4][128];
+  __shared__ float red[kRedSub][128];
   int l = 0;
   while (l + 1 < a.n_layers && (int)blockIdx.x >= a.blk_begin[l + 1]) ++l;
-  const int c = ((int)blockIdx.x - a.blk_begin[l]) * 128 + (threadIdx.x & 127);
-  const int sub = threadIdx.x >> 7, split = blockIdx.y;
+  const int col = threadIdx.x & 127, sub = threadIdx.x >> 7, split = blockIdx.y;
+  const int c = ((int)blockIdx.x - a.blk_begin[l]) * 128 + col;
   const int per = a.rows_pad / kGradSplits;
   const int r0 = split * per, r1 = r0 + per;
+  const float *zh = a.dZ[l], *zl = a.dZ[l] + a.plane[l];
+  const int ld = a.ld[l];
   float acc = 0.f;
-  if (c < a.Np[l])
-    for (int n = r0 + sub; n < r1; n += 4) {
-      const long long o = (long long)n * a.ld[l] + c;
-      acc += a.dZ[l][o] + a.dZ[l][o + a.plane[l]];
+  if (c < a.Np[l]) {
+#pragma unroll 8
+    for (int n = r0 + sub; n < r1; n += kRedSub) {
+      const long long o = (long long)n * ld + c;
+      acc += zh[o] + zl[o];
     }
-  red[sub][threadIdx.x & 127] = acc;
-  __syncthreads();
-  if (sub == 0 && c < a.Np[l])
-    a.gpart[(long long)split * a.gpart_stride + a.b_off[l] + c] =
-        (red[0][threadIdx.x] + red[1][threadIdx.x]) + (red[2][threadIdx.x] + red[3][threadIdx.x]);
-}
-
-// Inverting gradients (dqn.cpp:927-957) on the critic's input diff columns [S, S+10).
-struct InvertArgs {
-  int B, Bp, S, ldin;
-  const float *d_in;           // [Bp][ldin] fp32: dL/d(critic input)
-  const float *a16;            // actor outputs [Bp][16]
-  float *d16;                  // out: top diffs of the actor heads [Bp][16]
-  float *tap_raw, *tap_inv;    // [Bp][10] debug taps
-};
-__global__ void __launch_bounds__(256) invert_kernel(const InvertArgs a) {
-  DQNB_PDL_PROLOGUE();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= a.Bp * 16) return;
-  const int n = i >> 4, h = i & 15;
-  float diff = 0.f;
-  if (n < a.B && h < kActorOut) {
-    diff = a.d_in[(long long)n * a.ldin + a.S + h];
-    a.tap_raw[n * kActorOut + h] = diff;
-    const float output = a.a16[i];
-    float mn, mx;
-    if (h < kActionSize) { mn = -1.0f; mx = 1.0f; }
-    else if (h == kActionSize + 0 || h == kActionSize + 4) { mn = 0.f; mx = 100.f; }
-    else { mn = -180.f; mx = 180.f; }
-    if (diff < 0) diff *= (mx - output) / (mx - mn);
-    else if (diff > 0) diff *= (output - mn) / (mx - mn);
-    a.tap_inv[n * kActorOut + h] = diff;
   }
-  a.d16[i] = diff;
+  red[sub][col] = acc;
+  __syncthreads();
+  if (sub == 0 && c < a.Np[l]) {
+    float s = 0.f;
+#pragma unroll
+    for (int t = 0; t < kRedSub; ++t) s += red[t][col];
+    a.gpart[(long long)split * a.gpart_stride + a.b_off[l] + c] = s;
+  }
 }
 
 // -------------------------------------------------------------------------------------------
@@ -428,7 +518,28 @@ struct AdamArgs {
   const StepState *st; StepState *st_out;
   int is_critic;
   HyperParams hp;
+  // set on the last optimiser launch of an update: the block that finishes last publishes
+  // (critic_loss, avg_q) and advances the iteration / sampler counters (formerly finalize_kernel)
+  int finalize; unsigned int *ticket; const float *g_critic_tail, *g_actor_tail; float *results; int max_slots;
 };
+__device__ __forceinline__ void adam_finalize(const AdamArgs &a) {
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  const unsigned int done = atomicAdd(a.ticket, 1u);
+  if (done != gridDim.x - 1) return;
+  *a.ticket = 0;
+  StepState *st = a.st_out;
+  const int slot = st->result_slot;
+  if (slot < a.max_slots) {
+    a.results[2 * slot + 0] = a.g_critic_tail[0];   // critic_loss (dqn.cpp:905)
+    a.results[2 * slot + 1] = a.g_actor_tail[0];    // avg_q       (dqn.cpp:915)
+  }
+  st->result_slot = slot + 1;
+  st->critic_iter += 1;                             // Solver::Step ++iter_ (dqn.cpp:904)
+  st->actor_iter += 1;                              // set_iter(iter+1)     (dqn.cpp:965)
+  st->step += 1;
+}
 __global__ void __launch_bounds__(256) adam_kernel(const AdamArgs a) {
   DQNB_PDL_PROLOGUE();
   __shared__ float s_scale;
@@ -449,7 +560,10 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamArgs a) {
     __syncthreads();
   }
   const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  if (i >= a.flat) return;
+  if (i >= a.flat) {
+    if (a.finalize) adam_finalize(a);
+    return;
+  }
   const float scale = s_scale;
   const float step = a.is_critic ? a.st->step_critic : a.st->step_actor;
   const int do_soft = a.st->do_soft;
@@ -493,6 +607,7 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamArgs a) {
     *reinterpret_cast<float4 *>(a.T + i) = make_float4(oh[0], oh[1], oh[2], oh[3]);
     *reinterpret_cast<float4 *>(a.T + a.t_plane + i) = make_float4(ol[0], ol[1], ol[2], ol[3]);
   }
+  if (a.finalize) adam_finalize(a);
 }
 
 // split an fp32 array into (hi, lo) planes / join it back (parameter import / export)
