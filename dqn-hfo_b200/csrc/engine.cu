@@ -357,14 +357,18 @@ static int op_dx(const dqnb_config &cfg, const NetGeom &g, int l, const float *P
 }
 // input diff of layer 0 (critic policy pass): d_in = dZ_0 W_0, raw fp32
 static int op_dx_plain(const dqnb_config &cfg, const NetGeom &g, const float *P, const SplitMat &dZ0,
-                       float *d_in, Op *op) {
+                       float *d_in, long long split_stride, int *splits_out, Op *op) {
   const LayerGeom &L = g.L[0];
   GemmParams &p = op->gemm.p;
   memset(&p, 0, sizeof(p));
-  p.M = dZ0.rows; p.N = L.Kp; p.K = L.Np; p.a_mn = 0; p.b_mn = 1; p.splits = 1; p.epi = EPI_PLAIN;
+  p.M = dZ0.rows; p.N = L.Kp; p.K = L.Np; p.a_mn = 0; p.b_mn = 1; p.epi = EPI_PLAIN;
+  // few output tiles (the critic input is narrow) but a long contraction: split-K, partial planes
+  // are summed by the consumer (actor_head_bwd_kernel)
+  p.splits = pick_splits(((p.M + BM - 1) / BM) * ((p.N + 63) / 64), p.K / BK, kGradSplits);
+  *splits_out = p.splits;
   p.A = dZ0.p; p.a_plane = dZ0.plane(); p.lda = dZ0.ld;
   p.B = P + L.w_off; p.b_plane = g.flat; p.ldb = L.Kp;
-  p.out = d_in; p.out_split_stride = 0; p.ldo = L.Kp;
+  p.out = d_in; p.out_split_stride = split_stride; p.ldo = L.Kp;
   return finish_gemm(cfg, op);
 }
 // weight gradient of layer l: dW_l = dZ_l^T X_{l-1} (contraction over the minibatch, split-K)
@@ -532,9 +536,7 @@ static int build_backward(dqnb_handle_s *h, const NetGeom &g, const float *P, co
   }
   if (want_dw) {
     Op op;
-    op.kind = Op::COLSUM;
-    op.branch = 1;
-    op.wait_ev = 0;                                             // all dZ exist once dZ[0] does
+    op.kind = Op::COLSUM;                                       // main stream: every dZ exists after the dX chain
     ColsumArgs &a = op.cs;
     memset(&a, 0, sizeof(a));
     a.n_layers = g.n_hidden; a.rows_pad = h->Bp;
@@ -546,7 +548,6 @@ static int build_backward(dqnb_handle_s *h, const NetGeom &g, const float *P, co
     a.blk_begin[g.n_hidden] = blk;
     a.gpart = h->Gpart[g.critic]; a.gpart_stride = h->gpart_stride[g.critic];
     op.grid = dim3(blk, kGradSplits);
-    if (g.n_hidden == 1) op.wait_ev = -1;
     ops.push_back(op);
     SegTable &T = *segs;
     const int hs = 2 * g.n_hidden;
@@ -673,13 +674,15 @@ static int build_update_ops(dqnb_handle_s *h) {
   push_critic_head(h, QMODE_POLICY, PC, h->actC[topC], h->q_pi, ops);       // dqn.cpp:918-921
   // dqn.cpp:923 critic.BackwardFrom(q_values_layer): only the input diff is consumed
   if (build_backward(h, gC, PC, h->Xcp, h->actC, false, nullptr, nullptr, ops)) return -1;
-  if (op_dx_plain(h->cfg, gC, PC, h->dZ[0], h->d_in, &op)) return -1;
+  int din_splits = 1;
+  if (op_dx_plain(h->cfg, gC, PC, h->dZ[0], h->d_in, (long long)h->Bp * h->Kc, &din_splits, &op)) return -1;
   ops.push_back(op);
   op.kind = Op::ACTOR_HEAD_BWD;                                  // dqn.cpp:927-961 inverting gradients + ShareDiff
   {
     ActorHeadBwdArgs &a = op.ahb;
     memset(&a, 0, sizeof(a));
-    a.B = h->B; a.rows_pad = h->Bp; a.S = h->S; a.ldin = h->Kc; a.d_in = h->d_in; a.a16 = h->a16_pi; a.d16 = h->d16a;
+    a.B = h->B; a.rows_pad = h->Bp; a.S = h->S; a.ldin = h->Kc; a.d_in = h->d_in; a.din_splits = din_splits;
+    a.din_stride = (long long)h->Bp * h->Kc; a.a16 = h->a16_pi; a.d16 = h->d16a;
     a.tap_raw = h->tap_raw; a.tap_inv = h->tap_inv;
     a.W = PA + gA.hw_off; a.w_plane = gA.flat; a.Kp = gA.Hp;
     a.H = h->actA[topA].p; a.h_plane = h->actA[topA].plane(); a.ldh = h->actA[topA].ld;
@@ -817,7 +820,7 @@ static int create_impl(const dqnb_config *cfg, dqnb_handle_s *h) {
   const int rows16 = std::max(h->Bp, h->An);
   float **m16[] = {&h->a16_t, &h->a16_pi, &h->d16c, &h->d16a, &h->out16_act};
   for (float **v : m16) if (dalloc(h, v, (size_t)rows16 * 16)) return -1;
-  if (dalloc(h, &h->d_in, (size_t)h->Bp * h->Kc) || dalloc(h, &h->tap_raw, (size_t)h->Bp * kActorOut) || dalloc(h, &h->tap_inv, (size_t)h->Bp * kActorOut)) return -1;
+  if (dalloc(h, &h->d_in, (size_t)kGradSplits * h->Bp * h->Kc) || dalloc(h, &h->tap_raw, (size_t)h->Bp * kActorOut) || dalloc(h, &h->tap_inv, (size_t)h->Bp * kActorOut)) return -1;
   for (int l = 0; l < c.n_hidden; ++l) {
     const int Np = h->gA.L[l].Np;
     if (alloc_mat(h, &h->actAT[l], h->Bp, Np) || alloc_mat(h, &h->actCT[l], h->Bp, Np) || alloc_mat(h, &h->actC[l], h->Bp, Np) ||

@@ -312,7 +312,8 @@ __global__ void __launch_bounds__(256) critic_head_kernel(const CriticHeadArgs a
 //   dZ[n][k] = (sum_j d10[n][j] * W[j][k]) * relu'(h[n][k])
 struct ActorHeadBwdArgs {
   int B, rows_pad, S, ldin;
-  const float *d_in;           // [Bp][ldin] fp32: dL/d(critic input)
+  const float *d_in;           // [din_splits][Bp][ldin] fp32 split-K partials of dL/d(critic input)
+  int din_splits; long long din_stride;
   const float *a16;            // actor outputs [Bp][16]
   float *d16;                  // out: top diffs of the actor heads [Bp][16] (for the head weight gradient)
   float *tap_raw, *tap_inv;    // [Bp][10] debug taps
@@ -327,7 +328,7 @@ __global__ void __launch_bounds__(256) actor_head_bwd_kernel(const ActorHeadBwdA
   if (n >= a.rows_pad) return;
   float diff = 0.f;
   if (n < a.B && lane < kActorOut) {
-    diff = a.d_in[(long long)n * a.ldin + a.S + lane];
+    for (int sp = 0; sp < a.din_splits; ++sp) diff += a.d_in[sp * a.din_stride + (long long)n * a.ldin + a.S + lane];
     a.tap_raw[n * kActorOut + lane] = diff;
     const float output = a.a16[(long long)n * 16 + lane];
     float mn, mx;

@@ -23,12 +23,28 @@ def relerr(a, b):
     return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30))
 
 
+def relerr_robust(a, b, frac=2e-3):
+    """relerr after discarding the `frac` largest element errors.
+
+    The nets are piecewise linear: a pre-activation within rounding error of zero takes slope 1 on one
+    side and 0.01 on the other (Caffe ReLU backward, `bottom_data > 0`), so two fp32 evaluations that
+    differ only in summation order can legitimately disagree on a handful of (row, unit) masks, which
+    moves that row's action gradient by percents.  Even the fp32 oracle differs from float64 autograd
+    this way for unlucky seeds.  The bulk of each tensor must still agree to the parity tolerance and
+    the number of outliers is bounded by `frac`."""
+    a, b = np.asarray(a, np.float64).ravel(), np.asarray(b, np.float64).ravel()
+    e = np.sort(np.abs(a - b)) / (np.abs(b).max() + 1e-30)
+    keep = max(1, int(np.ceil(e.size * (1.0 - frac))))
+    return float(e[keep - 1])
+
+
 def make_pair(S, B, hidden, mode="warm", gemm_mode=0, n_replay=None, seed=0, capacity=None, p_term=0.2,
               use_graph=1, **cfg_kw):
     """An oracle state and a device learner holding identical weights and replay contents."""
     P = pkg()
     rng = np.random.default_rng(seed)
-    ocfg = O.make_config(state_size=S, batch=B, hidden=hidden, **cfg_kw)
+    use_blas = cfg_kw.pop("use_blas", 0)
+    ocfg = O.make_config(state_size=S, batch=B, hidden=hidden, use_blas=use_blas, **cfg_kw)
     a0, c0 = O.init_params(ocfg, False, rng, mode), O.init_params(ocfg, True, rng, mode)
     if mode == "caffe":
         at, ct = a0.copy(), c0.copy()
