@@ -320,6 +320,16 @@ static int finish_gemm(const dqnb_config &cfg, Op *op) {
     // A
     const int a_rows = p.a_mn ? p.K : p.M, b_rows = p.b_mn ? p.K : p.N;
     if (p.bn != 64 && p.bn != 128) p.bn = 64;
+    // Forward / dX GEMMs with a long contraction but few output tiles: split K over a 2-CTA cluster
+    // (DSMEM reduction in the epilogue) so that the dependent chain sees half the mainloop latency.
+    {
+      const int tiles = ((p.M + BM - 1) / BM) * ((p.N + p.bn - 1) / p.bn);
+      if (p.epi != EPI_PLAIN && p.splits == 1 && p.K / BK >= 16 && 2 * tiles <= 148 && cfg.use_graph >= 0 &&
+          !getenv("DQNB_NO_CLUSTER_SPLITK")) {
+        p.cluster_k = 1;
+        p.splits = 2;
+      }
+    }
     if (make_tmap(&op->gemm.tmA, p.A, a_rows, p.lda, p.a_plane, p.a_mn ? 32 : BM, p.a_mn != 0)) return -1;
     if (make_tmap(&op->gemm.tmB, p.B, b_rows, p.ldb, p.b_plane, p.b_mn ? 32 : p.bn, p.b_mn != 0)) return -1;
     op->grid = dim3((p.N + p.bn - 1) / p.bn, (p.M + BM - 1) / BM, p.splits);
@@ -405,15 +415,21 @@ static void op_head_fwd(const NetGeom &g, const float *P, const SplitMat &H, int
 // launching: every kernel goes out with the programmatic-stream-serialization attribute (PDL);
 // the kernels call griddepcontrol.wait before touching global memory (kernels.cuh).
 // ---------------------------------------------------------------------------------------------
+static int g_cluster_z = 1;   // set around a launch that wants thread-block clusters of (1,1,z)
 template <typename... KArgs, typename... Args>
 static cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
                             Args &&...args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
+  if (g_cluster_z > 1) {
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = 1; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = (unsigned)g_cluster_z;
+    cfg.numAttrs = 2;
+  }
   return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
 }
 
@@ -421,9 +437,12 @@ static int launch_op(dqnb_handle_s *h, const Op &op, cudaStream_t s) {
   cudaError_t e = cudaSuccess;
   switch (op.kind) {
     case Op::GEMM:
-      if (h->cfg.gemm_mode == DQNB_GEMM_TCGEN05_3XTF32)
+      if (h->cfg.gemm_mode == DQNB_GEMM_TCGEN05_3XTF32) {
+        g_cluster_z = op.gemm.p.cluster_k ? 2 : 1;
         e = launch_k(tc_kernel_for(op.gemm.p.a_mn, op.gemm.p.b_mn, op.gemm.p.bn), op.grid, dim3(TC_THREADS),
                      (size_t)tc_smem_for(op.gemm.p.bn), s, op.gemm);
+        g_cluster_z = 1;
+      }
       else
         e = launch_k(gemm_simt_kernel, op.grid, dim3(256), 0, s, op.gemm.p);
       break;
@@ -435,7 +454,7 @@ static int launch_op(dqnb_handle_s *h, const Op &op, cudaStream_t s) {
     case Op::HEAD_FWD: e = launch_k(head_fwd_kernel, dim3(op.blocks), dim3(256), 0, s, op.head); break;
     case Op::CRITIC_HEAD: e = launch_k(critic_head_kernel, dim3(op.blocks), dim3(256), 0, s, op.ch); break;
     case Op::ACTOR_HEAD_BWD: e = launch_k(actor_head_bwd_kernel, dim3(op.blocks), dim3(256), 0, s, op.ahb); break;
-    case Op::HEAD_BWD_W: e = launch_k(head_bwd_w_kernel, op.grid, dim3(1024), 0, s, op.hbw); break;
+    case Op::HEAD_BWD_W: e = launch_k(head_bwd_w_kernel, op.grid, dim3(256), 0, s, op.hbw); break;
     case Op::COLSUM: e = launch_k(colsum_kernel, op.grid, dim3(1024), 0, s, op.cs); break;
     case Op::REDUCE: e = launch_k(reduce_kernel, dim3(op.blocks), dim3(256), 0, s, op.red); break;
     case Op::ADAM: e = launch_k(adam_kernel, dim3(op.blocks), dim3(256), 0, s, op.adam); break;
@@ -490,11 +509,16 @@ static int run_ops(dqnb_handle_s *h, const std::vector<Op> &ops, cudaStream_t s,
 // building the op lists
 // ---------------------------------------------------------------------------------------------
 static int build_forward(dqnb_handle_s *h, const NetGeom &g, const float *P, const SplitMat &X,
-                         SplitMat *acts, std::vector<Op> &ops) {
+                         SplitMat *acts, std::vector<Op> &ops, bool critical_chain = true) {
   const SplitMat *in = &X;
   for (int l = 0; l < g.n_hidden; ++l) {
     Op op;
     if (op_fwd(h->cfg, g, l, P, *in, acts[l], &op)) return -1;
+    if (!critical_chain && op.gemm.p.cluster_k) {
+      // side-branch passes run beside the critical chain: they should not grab twice the SMs for a
+      // latency that nobody waits on, so they keep one CTA per tile
+      op.gemm.p.cluster_k = 0; op.gemm.p.splits = 1; op.grid.z = 1;
+    }
     ops.push_back(op);
     in = &acts[l];
   }
@@ -616,7 +640,7 @@ static Op make_head_bwd_w(dqnb_handle_s *h, const NetGeom &g, const float *d16, 
   memset(&b, 0, sizeof(b));
   b.d16 = d16; b.J = g.head_real; b.H = Htop.p; b.h_plane = Htop.plane(); b.ldh = Htop.ld; b.Kp = g.Hp;
   b.rows_pad = h->Bp; b.gpart = h->Gpart[g.critic]; b.gpart_stride = h->gpart_stride[g.critic]; b.hw_off = g.hw_off; b.hb_off = g.hb_off;
-  w.grid = dim3((g.Hp + 127) / 128, kGradSplits);
+  w.grid = dim3((g.Hp + kHbwCols - 1) / kHbwCols, kGradSplits);
   return w;
 }
 
@@ -649,12 +673,12 @@ static int build_update_ops(dqnb_handle_s *h) {
   op.kind = Op::FORK; ops.push_back(op);
   {
     const size_t mark = ops.size();
-    if (build_forward(h, gC, PC, h->Xc, h->actC, ops)) return -1;
+    if (build_forward(h, gC, PC, h->Xc, h->actC, ops, false)) return -1;
     for (size_t i = mark; i < ops.size(); ++i) ops[i].branch = 1;
   }
   {
     const size_t mark = ops.size();
-    if (build_forward(h, gA, PA, h->Xs, h->actA, ops)) return -1;
+    if (build_forward(h, gA, PA, h->Xs, h->actA, ops, false)) return -1;
     op_head_fwd(gA, PA, h->actA[topA], h->B, h->a16_pi, &h->Xcp, h->S, &op); ops.push_back(op);
     for (size_t i = mark; i < ops.size(); ++i) ops[i].branch = 2;
   }

@@ -38,6 +38,8 @@ struct GemmParams {
   const float *mask_hi; const float *mask_lo; int ldmask;  // EPI_DX
   int apply_lrelu;                            // EPI_FWD: 0 for linear layers
   int bn;                                     // N tile of the tcgen05 kernel: 64 or 128
+  int cluster_k;                              // 1: launched as 2-CTA clusters along z; the CTAs split K and the
+                                              //    leader adds its peer's partial tile over DSMEM before the epilogue
   int dbg;                                    // perf experiments (gemm_test only): bit0 skip MMA, bit1 skip TMA
   long long *dbg_clk;                         // optional: MMA-thread clock64 stamps {start, issued, complete}
 };
@@ -285,6 +287,16 @@ __device__ __forceinline__ unsigned long long gtime_ns() {
 // [3] first operands landed [4] accumulators complete [5] epilogue stores issued [6] kernel exit
 #define DQNB_STAMP(i) do { if (p.dbg_clk && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) p.dbg_clk[i] = (long long)gtime_ns(); } while (0)
 
+__device__ __forceinline__ void cluster_arrive_release() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait_acquire() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ float4 ld_dsmem_f4(uint32_t local_saddr, uint32_t rank) {
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_saddr), "r"(rank));
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(ra) : "memory");
+  return v;
+}
+
 // The warp roles run with the whole warp converged: every value feeding TMA / MMA issue is
 // warp-uniform (uniform registers, no per-thread descriptor arithmetic), and one elected lane
 // issues.  A single divergent thread doing that arithmetic costs ~300 cycles per k-step, 3x the
@@ -309,6 +321,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
   const int kb1 = min(kblocks, kb0 + per);
   const int iters = max(kb1 - kb0, 0);
   const uint32_t tfull = bars + 8 * (2 * STAGES);
+  const bool clus = p.cluster_k != 0;          // split-K over a 2-CTA cluster (blockIdx.z = cluster rank)
+  uint32_t crank = 0;
+  if (clus) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
   if (threadIdx.x == 0) DQNB_STAMP(0);
 
   if (warp == 0 && lane == 0) {
@@ -423,6 +438,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
     float *st_hi = reinterpret_cast<float *>(base_ptr) + (q * 32) * LDS;
     float *st_lo = st_hi + BM * LDS;
     const int n_base = n_tile * BN_;
+    if (clus && crank == 1) {
+      // split-K peer: publish the raw partial tile in this CTA's staging area; the leader reads it over
+      // distributed shared memory after cluster barrier #1 (below) and runs the real epilogue
+      if (iters > 0) { mbar_wait(tfull, 0); tc_fence_after(); }
+      float *mine = st_hi + lane * LDS;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN_; c0 += 32) {
+        uint32_t r[32], r2[32];
+        if (iters > 0) {
+          const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+          tmem_ld32(taddr, r);
+          tmem_ld32(taddr + BN_, r2);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { r[j] = 0u; r2[j] = 0u; }
+        }
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4 *>(mine + c0 + j) =
+              make_float4(__uint_as_float(r[j]) + __uint_as_float(r2[j]), __uint_as_float(r[j + 1]) + __uint_as_float(r2[j + 1]),
+                          __uint_as_float(r[j + 2]) + __uint_as_float(r2[j + 2]), __uint_as_float(r[j + 3]) + __uint_as_float(r2[j + 3]));
+      }
+    } else {
     if (p.epi == EPI_FWD) {                  // stage the tile's bias once (overlaps the mainloop)
       for (int t = et; t < BN_; t += 128) {
         const int n = n_base + t;
@@ -452,6 +491,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       mbar_wait(tfull, 0);
       tc_fence_after();
     }
+    if (clus) { cluster_arrive_release(); cluster_wait_acquire(); }   // barrier #1: the peer's partial is visible
     if (warp == 2 && lane == 0) DQNB_STAMP(4);
     if (p.epi == EPI_DX) {
       if (BN_ == 64) {
@@ -487,6 +527,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = 0.f;
+      }
+      if (clus) {                            // + the other half of K, from the peer CTA's shared memory
+        const uint32_t mine = smem_u32(my_hi + c0);
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 pp = ld_dsmem_f4(mine + j * 4, 1u);
+          v[j] += pp.x; v[j + 1] += pp.y; v[j + 2] += pp.z; v[j + 3] += pp.w;
+        }
       }
       if (p.epi == EPI_PLAIN) {
 #pragma unroll
@@ -533,6 +581,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       }
     }
     if (warp == 2 && lane == 0) DQNB_STAMP(5);
+    }   // !(cluster peer)
+  }
+  if (clus) {
+    // every thread of both CTAs passes two cluster barriers: #1 publishes the peer's partial tile (the
+    // leader's epilogue warps already passed it above), #2 keeps the peer's shared memory alive until the
+    // leader has read it
+    if (!(warp >= 2 && crank == 0)) { cluster_arrive_release(); cluster_wait_acquire(); }
+    cluster_arrive_release();
+    cluster_wait_acquire();
   }
   tc_fence_before();
   __syncthreads();

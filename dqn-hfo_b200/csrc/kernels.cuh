@@ -362,21 +362,22 @@ __global__ void __launch_bounds__(256) actor_head_bwd_kernel(const ActorHeadBwdA
 }
 
 // Head weight/bias gradients: dW[j][k] = sum_n d16[n][j] h[n][k] ; db[j] = sum_n d16[n][j].
-// grid (Kp/128, kGradSplits); 1024 threads = 8 row sub-groups x 128 columns; the split's d16 rows are
-// staged in shared memory once, the H loads are unrolled so several are in flight per thread.
+// grid (Kp/32, kGradSplits); 256 threads = 8 row sub-groups x 32 columns (many small blocks: the kernel
+// sits at the head of the gradient side chain, so its latency matters more than its efficiency).
 constexpr int kRedSub = 8;
+constexpr int kHbwCols = 32;
 struct HeadBwdWArgs {
   const float *d16; int J;
   const float *H; long long h_plane; int ldh; int Kp;
   int rows_pad;
   float *gpart; long long gpart_stride; long long hw_off, hb_off;
 };
-__global__ void __launch_bounds__(1024) head_bwd_w_kernel(const HeadBwdWArgs a) {
+__global__ void __launch_bounds__(256) head_bwd_w_kernel(const HeadBwdWArgs a) {
   DQNB_PDL_PROLOGUE();
-  __shared__ float red[kRedSub][kActorOut][128];
-  __shared__ float sd[128 * 16];             // up to 128 rows of d16 per split
-  const int col = threadIdx.x & 127, sub = threadIdx.x >> 7, split = blockIdx.y;
-  const int k = blockIdx.x * 128 + col;
+  __shared__ float red[kRedSub][kActorOut][kHbwCols];
+  __shared__ float sd[128 * 16];             // up to 128 rows of d16 per chunk
+  const int col = threadIdx.x & (kHbwCols - 1), sub = threadIdx.x / kHbwCols, split = blockIdx.y;
+  const int k = blockIdx.x * kHbwCols + col;
   const int per = a.rows_pad / kGradSplits;  // rows of this split (multiple of 16)
   const int r0 = split * per;
   float acc[kActorOut];
@@ -391,7 +392,7 @@ __global__ void __launch_bounds__(1024) head_bwd_w_kernel(const HeadBwdWArgs a) 
     if (sub == 0 && col < a.J)
       for (int n = 0; n < rows; ++n) bias_acc += sd[n * 16 + col];
     if (k < a.Kp) {
-#pragma unroll 4
+#pragma unroll 8
       for (int n = sub; n < rows; n += kRedSub) {
         const long long ho = (long long)(r0 + c0 + n) * a.ldh + k;
         const float x = a.H[ho] + a.H[ho + a.h_plane];
@@ -405,8 +406,7 @@ __global__ void __launch_bounds__(1024) head_bwd_w_kernel(const HeadBwdWArgs a) 
   for (int j = 0; j < kActorOut; ++j) red[sub][j][col] = acc[j];
   __syncthreads();
   float *g = a.gpart + (long long)split * a.gpart_stride;
-  // 1024 threads finish the (J x 128) outputs: thread -> (j = sub.., col)
-  for (int j = sub; j < a.J; j += kRedSub) {
+  for (int j = sub; j < a.J; j += kRedSub) {   // thread -> (j = sub, sub+8, .. ; col)
     if (k < a.Kp) {
       float s = 0.f;
 #pragma unroll
