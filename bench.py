@@ -317,10 +317,11 @@ def main():
         # dominant kernel: the layer GEMMs.  Timed live: all GEMM launches of one update, back to back.
         try:
             gemm_ms, n_gemm = gemm_only_time(pkg, d, reps=50)
+            traffic, traffic_src = ncu_traffic_per_launch()
             ach = fpt * B / (gemm_ms * 1e-3) / 1e12
             line["roofline"] = {
                 "bound": "tensor", "achieved": ach, "peak": bf16_sus, "unit": "TFLOP/s", "frac": ach / bf16_sus,
-                "traffic": None, "peak_source": f"{src} bf16_tflops_sustained (kernel timed inside a long step)",
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": f"{src} bf16_tflops_sustained (kernel timed inside a long step)",
                 "kernel": "dqnb::gemm_tc_kernel", "launches_per_step": n_gemm, "avg_launch_us": 1e3 * gemm_ms / n_gemm,
                 "algorithmic_flop_per_step": fpt * B,
                 "note": "3xTF32 issues 6 bf16-equivalent MMA passes per algorithmic product: ceiling = peak/6",
@@ -344,6 +345,24 @@ def main():
     d.close()
     if dist is not None:
         dist.destroy_process_group()
+
+
+def ncu_traffic_per_launch():
+    """dram__bytes_read.sum + dram__bytes_write.sum per gemm_tc_kernel launch, averaged over the launches of
+    the newest committed `ncu --set full` summary (profiles/*_ncu_gemm_full.txt).  None if no capture."""
+    import glob
+    import re
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_gemm_full.txt")), key=os.path.getmtime)
+    if not files:
+        return None, None
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot, n = 0.0, 0
+    for line in open(files[-1]):
+        m = re.match(r"\s*dram__bytes_(read|write)\.sum\s+([0-9.]+)\s+(\w+)", line)
+        if m:
+            tot += float(m.group(2)) * unit.get(m.group(3), 1.0)
+            n += m.group(1) == "read"
+    return (tot / n if n else None), os.path.basename(files[-1])
 
 
 def gemm_only_time(pkg, d, reps=50):

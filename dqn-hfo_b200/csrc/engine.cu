@@ -247,7 +247,7 @@ struct dqnb_handle_s {
   float *norm_part = nullptr; int n_norm[2] = {0, 0};
   double *scal_part = nullptr; int n_scal = 0;
   // replay ring
-  float *ring_s = nullptr, *ring_sn = nullptr, *ring_misc = nullptr;
+  float *ring = nullptr; int rw = 0;   // replay ring [cap][rw]: state Sp | next state Sp | act10, r, mc, terminal, pad
   int ring_head = 0, ring_size = 0;
   // minibatch buffers
   int32_t *idx = nullptr;
@@ -265,9 +265,10 @@ struct dqnb_handle_s {
   StepState *st = nullptr;
   float *results = nullptr; int max_slots = 4096;
   unsigned int *ticket = nullptr;
-  float *h_results = nullptr;
+  float *h_results = nullptr;       // mapped pinned ring the last optimiser launch writes (critic_loss, avg_q) into
+  unsigned long long host_step = 0;  // updates enqueued so far (mirrors StepState::step)
   // staging for replay appends
-  float *h_stage_s = nullptr, *h_stage_sn = nullptr, *h_stage_misc = nullptr; int stage_rows = 0;
+  float *h_stage = nullptr; int stage_rows = 0;   // pinned staging rows in ring layout (padding stays zero)
   // op lists + graphs
   std::vector<Op> update_ops, act_ops, eval_ops;
   cudaGraphExec_t graph_sampled = nullptr, graph_injected = nullptr;
@@ -659,7 +660,7 @@ static int build_update_ops(dqnb_handle_s *h) {
     GatherArgs &a = op.gather;
     memset(&a, 0, sizeof(a));
     a.st = h->st; a.idx = h->idx; a.sample = variant == 1; a.seed = h->cfg.seed; a.hp = h->hp;
-    a.ring_s = h->ring_s; a.ring_sn = h->ring_sn; a.ring_misc = h->ring_misc;
+    a.ring_s = h->ring; a.ring_sn = h->ring + h->Sp; a.ring_misc = h->ring + 2 * h->Sp; a.rw = h->rw;
     a.cap = h->cfg.replay_capacity; a.B = h->B; a.Bp = h->Bp; a.S = h->S; a.Sp = h->Sp; a.Kc = h->Kc;
     a.Xs = h->Xs.p; a.Xsn = h->Xsn.p; a.Xc = h->Xc.p; a.Xct = h->Xct.p; a.Xcp = h->Xcp.p;
     a.reward = h->reward; a.mc = h->mc; a.term = h->term;
@@ -835,7 +836,8 @@ static int create_impl(const dqnb_config *cfg, dqnb_handle_s *h) {
   if (dalloc(h, &h->scal_part, (size_t)h->n_scal)) return -1;
   // replay ring (rows padded to Sp floats = 256 B multiples: aligned, vectorisable gathers)
   const size_t cap = (size_t)c.replay_capacity;
-  if (dalloc(h, &h->ring_s, cap * h->Sp) || dalloc(h, &h->ring_sn, cap * h->Sp) || dalloc(h, &h->ring_misc, cap * kMiscStride)) return -1;
+  h->rw = 2 * h->Sp + kMiscStride;
+  if (dalloc(h, &h->ring, cap * h->rw)) return -1;
   if (dalloc(h, &h->idx, (size_t)h->Bp)) return -1;
   if (alloc_mat(h, &h->Xs, h->Bp, h->Sp) || alloc_mat(h, &h->Xsn, h->Bp, h->Sp) || alloc_mat(h, &h->Xc, h->Bp, h->Kc) ||
       alloc_mat(h, &h->Xct, h->Bp, h->Kc) || alloc_mat(h, &h->Xcp, h->Bp, h->Kc)) return -1;
@@ -852,11 +854,17 @@ static int create_impl(const dqnb_config *cfg, dqnb_handle_s *h) {
   }
   if (alloc_mat(h, &h->Xact, h->An, h->Sp) || alloc_mat(h, &h->Xeval, h->An, h->Kc)) return -1;
   if (halloc(h, &h->h_act_in, (size_t)2 * h->An * h->Kc) || halloc(h, &h->h_act_out, (size_t)h->An * 16)) return -1;
-  if (dalloc(h, &h->st, 1) || dalloc(h, &h->results, (size_t)2 * h->max_slots) || dalloc(h, &h->ticket, 1)) return -1;
-  if (halloc(h, &h->h_results, (size_t)2 * h->max_slots)) return -1;
+  if (dalloc(h, &h->st, 1) || dalloc(h, &h->ticket, 1)) return -1;
+  {   // results live in mapped pinned host memory: reading them back needs a stream sync, no copy
+    void *hp = nullptr, *dp = nullptr;
+    DQNB_CUDA(cudaHostAlloc(&hp, sizeof(float) * 2 * h->max_slots, cudaHostAllocMapped));
+    memset(hp, 0, sizeof(float) * 2 * h->max_slots);
+    h->pinned.push_back(hp);
+    DQNB_CUDA(cudaHostGetDevicePointer(&dp, hp, 0));
+    h->h_results = (float *)hp; h->results = (float *)dp;
+  }
   h->stage_rows = 4096;
-  if (halloc(h, &h->h_stage_s, (size_t)h->stage_rows * h->Sp) || halloc(h, &h->h_stage_sn, (size_t)h->stage_rows * h->Sp) ||
-      halloc(h, &h->h_stage_misc, (size_t)h->stage_rows * kMiscStride)) return -1;
+  if (halloc(h, &h->h_stage, (size_t)h->stage_rows * h->rw)) return -1;
   if (build_update_ops(h) || build_act_ops(h)) return -1;
   if (getenv("DQNB_TRACE")) {
     h->trace_ops = (int)h->update_ops.size();
@@ -1018,29 +1026,26 @@ static int push_ring_state(dqnb_handle h) {
 
 static int append_rows(dqnb_handle h, int32_t n, const float *s, const float *act10, const float *reward,
                        const float *mc, const float *s_next, const uint8_t *terminal) {
-  const int cap = h->cfg.replay_capacity, S = h->S, Sp = h->Sp;
+  const int cap = h->cfg.replay_capacity, S = h->S, Sp = h->Sp, rw = h->rw;
   int done = 0;
   while (done < n) {
     const int chunk = std::min(n - done, h->stage_rows);
-    DQNB_CUDA(cudaStreamSynchronize(h->stream));   // staging buffers are reused
-    for (int i = 0; i < chunk; ++i) {
+    DQNB_CUDA(cudaStreamSynchronize(h->stream));   // the staging buffer is reused
+    for (int i = 0; i < chunk; ++i) {              // padding columns of the staging rows are zero for good
       const int r = done + i;
-      float *ds = h->h_stage_s + (size_t)i * Sp, *dn = h->h_stage_sn + (size_t)i * Sp, *dm = h->h_stage_misc + (size_t)i * kMiscStride;
-      memcpy(ds, s + (size_t)r * S, sizeof(float) * S);
-      memset(ds + S, 0, sizeof(float) * (Sp - S));
+      float *row = h->h_stage + (size_t)i * rw;
+      memcpy(row, s + (size_t)r * S, sizeof(float) * S);
       const bool t = terminal[r] != 0;
-      if (!t && s_next) memcpy(dn, s_next + (size_t)r * S, sizeof(float) * S); else memset(dn, 0, sizeof(float) * S);
-      memset(dn + S, 0, sizeof(float) * (Sp - S));
+      if (!t && s_next) memcpy(row + Sp, s_next + (size_t)r * S, sizeof(float) * S); else memset(row + Sp, 0, sizeof(float) * S);
+      float *dm = row + 2 * Sp;
       memcpy(dm, act10 + (size_t)r * kActorOut, sizeof(float) * kActorOut);
-      dm[10] = reward[r]; dm[11] = mc[r]; dm[12] = t ? 1.f : 0.f; dm[13] = dm[14] = dm[15] = 0.f;
+      dm[10] = reward[r]; dm[11] = mc[r]; dm[12] = t ? 1.f : 0.f;
     }
     int tail = (h->ring_head + h->ring_size) % cap;
     int left = chunk, src = 0;
-    while (left > 0) {
+    while (left > 0) {                              // one copy per contiguous run (two when the ring wraps)
       const int run = std::min(left, cap - tail);
-      DQNB_CUDA(cudaMemcpyAsync(h->ring_s + (size_t)tail * Sp, h->h_stage_s + (size_t)src * Sp, sizeof(float) * (size_t)run * Sp, cudaMemcpyHostToDevice, h->stream));
-      DQNB_CUDA(cudaMemcpyAsync(h->ring_sn + (size_t)tail * Sp, h->h_stage_sn + (size_t)src * Sp, sizeof(float) * (size_t)run * Sp, cudaMemcpyHostToDevice, h->stream));
-      DQNB_CUDA(cudaMemcpyAsync(h->ring_misc + (size_t)tail * kMiscStride, h->h_stage_misc + (size_t)src * kMiscStride, sizeof(float) * (size_t)run * kMiscStride, cudaMemcpyHostToDevice, h->stream));
+      DQNB_CUDA(cudaMemcpyAsync(h->ring + (size_t)tail * rw, h->h_stage + (size_t)src * rw, sizeof(float) * (size_t)run * rw, cudaMemcpyHostToDevice, h->stream));
       tail = (tail + run) % cap; src += run; left -= run;
     }
     h->ring_size += chunk;
@@ -1086,21 +1091,18 @@ int dqnb_get_transitions(dqnb_handle h, int32_t first, int32_t n, float *s, floa
   DQNB_CUDA(cudaSetDevice(h->cfg.device));
   DQNB_CUDA(cudaStreamSynchronize(h->stream));
   const int cap = h->cfg.replay_capacity, S = h->S, Sp = h->Sp;
-  std::vector<float> bs((size_t)Sp), bn((size_t)Sp), bm(kMiscStride);
-  // row-at-a-time is fine here: this is the snapshot path, not the hot path
-  std::vector<float> rs((size_t)n * Sp), rn((size_t)n * Sp), rm((size_t)n * kMiscStride);
+  const int rw = h->rw;
+  std::vector<float> rows((size_t)n * rw);
   int phys = (h->ring_head + first) % cap, left = n, dst = 0;
   while (left > 0) {
     const int run = std::min(left, cap - phys);
-    DQNB_CUDA(cudaMemcpy(rs.data() + (size_t)dst * Sp, h->ring_s + (size_t)phys * Sp, sizeof(float) * (size_t)run * Sp, cudaMemcpyDeviceToHost));
-    DQNB_CUDA(cudaMemcpy(rn.data() + (size_t)dst * Sp, h->ring_sn + (size_t)phys * Sp, sizeof(float) * (size_t)run * Sp, cudaMemcpyDeviceToHost));
-    DQNB_CUDA(cudaMemcpy(rm.data() + (size_t)dst * kMiscStride, h->ring_misc + (size_t)phys * kMiscStride, sizeof(float) * (size_t)run * kMiscStride, cudaMemcpyDeviceToHost));
+    DQNB_CUDA(cudaMemcpy(rows.data() + (size_t)dst * rw, h->ring + (size_t)phys * rw, sizeof(float) * (size_t)run * rw, cudaMemcpyDeviceToHost));
     phys = (phys + run) % cap; dst += run; left -= run;
   }
   for (int i = 0; i < n; ++i) {
-    if (s) memcpy(s + (size_t)i * S, rs.data() + (size_t)i * Sp, sizeof(float) * S);
-    if (s_next) memcpy(s_next + (size_t)i * S, rn.data() + (size_t)i * Sp, sizeof(float) * S);
-    const float *m = rm.data() + (size_t)i * kMiscStride;
+    const float *row = rows.data() + (size_t)i * rw, *m = row + 2 * Sp;
+    if (s) memcpy(s + (size_t)i * S, row, sizeof(float) * S);
+    if (s_next) memcpy(s_next + (size_t)i * S, row + Sp, sizeof(float) * S);
     if (act10) memcpy(act10 + (size_t)i * kActorOut, m, sizeof(float) * kActorOut);
     if (reward) reward[i] = m[10];
     if (mc_target) mc_target[i] = m[11];
@@ -1127,6 +1129,7 @@ static int ensure_graph(dqnb_handle h, bool injected) {
 }
 
 static int enqueue_update(dqnb_handle h, bool injected) {
+  h->host_step += 1;
   if (h->cfg.use_graph) {
     if (ensure_graph(h, injected)) return -1;
     DQNB_CUDA(cudaGraphLaunch(injected ? h->graph_injected : h->graph_sampled, h->stream));
@@ -1139,18 +1142,14 @@ static int enqueue_update(dqnb_handle h, bool injected) {
   return 0;
 }
 
-static int reset_slots(dqnb_handle h) {
-  const int zero = 0;
-  DQNB_CUDA(cudaMemcpyAsync(&h->st->result_slot, &zero, sizeof(int), cudaMemcpyHostToDevice, h->stream));
-  return 0;
-}
-
+// (critic_loss, avg_q) of the last n updates: the optimiser launch of update k wrote slot k % max_slots of
+// the mapped pinned ring; a stream sync makes them visible
 static int fetch_results(dqnb_handle h, int n, float *critic_loss, float *avg_q) {
-  DQNB_CUDA(cudaMemcpyAsync(h->h_results, h->results, sizeof(float) * 2 * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
   DQNB_CUDA(cudaStreamSynchronize(h->stream));
   for (int i = 0; i < n; ++i) {
-    if (critic_loss) critic_loss[i] = h->h_results[2 * i];
-    if (avg_q) avg_q[i] = h->h_results[2 * i + 1];
+    const int slot = (int)((h->host_step - (unsigned long long)n + i) % (unsigned long long)h->max_slots);
+    if (critic_loss) critic_loss[i] = h->h_results[2 * slot];
+    if (avg_q) avg_q[i] = h->h_results[2 * slot + 1];
   }
   return 0;
 }
@@ -1163,7 +1162,6 @@ int dqnb_update(dqnb_handle h, int32_t n_updates, float *critic_loss, float *avg
   int done = 0;
   while (done < n_updates) {
     const int chunk = std::min(n_updates - done, h->max_slots);
-    if (reset_slots(h)) return -1;
     for (int i = 0; i < chunk; ++i) if (enqueue_update(h, false)) return -1;
     if (fetch_results(h, chunk, critic_loss ? critic_loss + done : nullptr, avg_q ? avg_q + done : nullptr)) return -1;
     done += chunk;
@@ -1177,7 +1175,6 @@ int dqnb_update_with_indices(dqnb_handle h, const int32_t *idx, float *critic_lo
   for (int i = 0; i < h->B; ++i)
     if (idx[i] < 0 || idx[i] >= h->ring_size) DQNB_FAIL("index %d out of range [0,%d)", idx[i], h->ring_size);
   DQNB_CUDA(cudaMemcpyAsync(h->idx, idx, sizeof(int32_t) * h->B, cudaMemcpyHostToDevice, h->stream));
-  if (reset_slots(h)) return -1;
   if (enqueue_update(h, true)) return -1;
   return fetch_results(h, 1, critic_loss, avg_q);
 }
@@ -1187,7 +1184,6 @@ int dqnb_benchmark(dqnb_handle h, int32_t n_updates, float *elapsed_ms) {
   if (h->ring_size <= 0) DQNB_FAIL("Benchmark on an empty replay memory");
   DQNB_CUDA(cudaSetDevice(h->cfg.device));
   if (h->cfg.use_graph && ensure_graph(h, false)) return -1;
-  if (reset_slots(h)) return -1;
   DQNB_CUDA(cudaStreamSynchronize(h->stream));
   DQNB_CUDA(cudaEventRecord(h->ev0, h->stream));
   for (int i = 0; i < n_updates; ++i) if (enqueue_update(h, false)) return -1;

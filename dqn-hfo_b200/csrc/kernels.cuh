@@ -84,7 +84,8 @@ struct GatherArgs {
   int sample;                  // 1: draw idx on the device (SampleTransitionsFromMemory, dqn.cpp:501-509)
   unsigned long long seed;
   HyperParams hp;
-  const float *ring_s, *ring_sn, *ring_misc;
+  const float *ring_s, *ring_sn, *ring_misc;   // one row-interleaved ring: [state Sp | next Sp | misc 16]
+  int rw;                      // floats per ring row
   int cap, B, Bp, S, Sp, Kc;
   float *Xs, *Xsn;           // [2][Bp][Sp]   actor inputs: s, s'
   float *Xc, *Xct, *Xcp;     // [2][Bp][Kc]   critic inputs: (s,a,p), (s',.), (s,.)
@@ -120,15 +121,15 @@ __global__ void __launch_bounds__(128) gather_kernel(const GatherArgs a) {
       id = a.idx[n];
     }
     phys = ((long long)a.st->ring_head + id) % a.cap;
-    misc_term = a.ring_misc[phys * kMiscStride + 12];
+    misc_term = a.ring_misc[phys * a.rw + 12];
   }
   const bool has_next = valid && misc_term == 0.f;
   const long long pS = (long long)a.Bp * a.Sp, pK = (long long)a.Bp * a.Kc;
   for (int c = threadIdx.x; c < a.Kc; c += blockDim.x) {
     float sv = 0.f, snv = 0.f;
     if (c < a.Sp) {
-      if (valid) sv = a.ring_s[phys * a.Sp + c];
-      if (has_next) snv = a.ring_sn[phys * a.Sp + c];
+      if (valid) sv = a.ring_s[phys * a.rw + c];
+      if (has_next) snv = a.ring_sn[phys * a.rw + c];
       const long long o = (long long)n * a.Sp + c;
       float h = tf32_hi(sv);
       a.Xs[o] = h; a.Xs[o + pS] = sv - h;
@@ -137,7 +138,7 @@ __global__ void __launch_bounds__(128) gather_kernel(const GatherArgs a) {
     }
     float xc = 0.f;
     if (c < a.S) xc = sv;
-    else if (c < a.S + kActorOut && valid) xc = a.ring_misc[phys * kMiscStride + (c - a.S)];
+    else if (c < a.S + kActorOut && valid) xc = a.ring_misc[phys * a.rw + (c - a.S)];
     const long long o = (long long)n * a.Kc + c;
     float h = tf32_hi(xc);
     a.Xc[o] = h; a.Xc[o + pK] = xc - h;
@@ -149,8 +150,8 @@ __global__ void __launch_bounds__(128) gather_kernel(const GatherArgs a) {
     a.Xcp[o] = h; a.Xcp[o + pK] = xp - h;
   }
   if (threadIdx.x == 0) {
-    a.reward[n] = valid ? a.ring_misc[phys * kMiscStride + 10] : 0.f;
-    a.mc[n] = valid ? a.ring_misc[phys * kMiscStride + 11] : 0.f;
+    a.reward[n] = valid ? a.ring_misc[phys * a.rw + 10] : 0.f;
+    a.mc[n] = valid ? a.ring_misc[phys * a.rw + 11] : 0.f;
     a.term[n] = misc_term;
   }
 }
@@ -531,12 +532,9 @@ __device__ __forceinline__ void adam_finalize(const AdamArgs &a) {
   if (done != gridDim.x - 1) return;
   *a.ticket = 0;
   StepState *st = a.st_out;
-  const int slot = st->result_slot;
-  if (slot < a.max_slots) {
-    a.results[2 * slot + 0] = a.g_critic_tail[0];   // critic_loss (dqn.cpp:905)
-    a.results[2 * slot + 1] = a.g_actor_tail[0];    // avg_q       (dqn.cpp:915)
-  }
-  st->result_slot = slot + 1;
+  const int slot = (int)(st->step % (unsigned long long)a.max_slots);   // host-visible ring (mapped pinned memory)
+  a.results[2 * slot + 0] = a.g_critic_tail[0];     // critic_loss (dqn.cpp:905)
+  a.results[2 * slot + 1] = a.g_actor_tail[0];      // avg_q       (dqn.cpp:915)
   st->critic_iter += 1;                             // Solver::Step ++iter_ (dqn.cpp:904)
   st->actor_iter += 1;                              // set_iter(iter+1)     (dqn.cpp:965)
   st->step += 1;
