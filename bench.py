@@ -202,7 +202,9 @@ def workload_config(args, world):
                     f"batch {args.batch} UpdateActorCritic per GPU",
         "state_size": args.state_size, "batch_per_gpu": args.batch, "global_batch": args.batch * world,
         "hidden": list(args.hidden), "replay_transitions": args.replay,
-        "parallelism": f"dp{world} (replay sharded, NCCL gradient all-reduce)" if world > 1 else "single GPU",
+        "parallelism": (f"dp{world} (replay sharded; gradient exchange: " +
+                        ("fused reduce-scatter/all-gather kernel over NVLink peer memory)" if getattr(args, "comm", "p2p") == "p2p"
+                         else "ncclAllReduce)")) if world > 1 else "single GPU",
         "precision": "3xTF32 split-fp32 operands on tcgen05 (fp32-faithful: parity mode == benchmarked mode)",
         "l2": "replay ring (0.6 GB) exceeds L2; weights/activations are L2-resident by design of the workload",
     }
@@ -221,6 +223,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gemm-mode", type=int, default=0)
+    ap.add_argument("--comm", default="p2p", choices=["p2p", "nccl"], help="gradient exchange for --gpus > 1")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -244,12 +247,17 @@ def main():
     rows = max(args.replay // world, 4 * B)
     d = pkg.DQNB(device=local, state_size=S, batch=B, hidden=hidden, replay_capacity=rows + B + 8,
                  seed=3 + rank, world_size=world, rank=rank, gemm_mode=args.gemm_mode, max_act_batch=64)
-    if world > 1:
+    if world > 1 and args.comm == "nccl":
         idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
             idt.copy_(torch.frombuffer(bytearray(pkg.comm_unique_id()), dtype=torch.uint8))
         dist.broadcast(idt, 0)
         d.comm_init(bytes(idt.cpu().numpy().tobytes()))
+    elif world > 1:   # product path: fused reduce-scatter + all-gather kernel over NVLink peer memory (CUDA IPC)
+        mine = torch.frombuffer(bytearray(d.comm_p2p_handle()), dtype=torch.uint8).cuda()
+        allh = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allh, mine)
+        d.comm_p2p_init(b"".join(bytes(t.cpu().numpy().tobytes()) for t in allh))
     d.init_params(seed=2, std=0.01)      # identical replicas: same seed on every rank
     s, a, r, mc, term, sn = synth_replay(rows, S, seed=1 + rank)
     for i in range(0, rows, 65536):
@@ -342,6 +350,11 @@ def main():
                 "ms_per_update": per * 1e3,
             }
         print(json.dumps(line))
+    if world > 1 and d.comm_status() != 0:
+        raise SystemExit("gradient exchange timed out on a peer: the run is invalid")
+    if dist is not None:
+        torch.cuda.synchronize()
+        dist.barrier()
     d.close()
     if dist is not None:
         dist.destroy_process_group()

@@ -86,6 +86,9 @@ def lib():
     L.dqnb_evaluate.argtypes = [H, C.c_int32, fp, fp, fp]
     L.dqnb_comm_unique_id.argtypes = [C.c_void_p]
     L.dqnb_comm_init.argtypes = [H, C.c_void_p]
+    L.dqnb_comm_p2p_handle.argtypes = [H, C.c_void_p]
+    L.dqnb_comm_p2p_init.argtypes = [H, C.c_void_p]
+    L.dqnb_comm_status.argtypes = [H]
     L.dqnb_sync.argtypes = [H]
     L.dqnb_kernel_launches.argtypes = [H]
     L.dqnb_kernel_launches.restype = C.c_int64
@@ -104,7 +107,8 @@ EXPORTS = [
     "dqnb_update", "dqnb_update_with_indices", "dqnb_benchmark", "dqnb_benchmark_gemms",
     "dqnb_peek_sample_indices",
     "dqnb_select_actions", "dqnb_select_actions_async", "dqnb_select_actions_wait", "dqnb_evaluate",
-    "dqnb_comm_unique_id", "dqnb_comm_init", "dqnb_sync", "dqnb_kernel_launches", "dqnb_debug_read",
+    "dqnb_comm_unique_id", "dqnb_comm_init", "dqnb_comm_p2p_handle", "dqnb_comm_p2p_init", "dqnb_comm_status",
+    "dqnb_sync", "dqnb_kernel_launches", "dqnb_debug_read",
     "dqnb_gemm_test",
 ]
 
@@ -289,6 +293,18 @@ class DQNB:
     def comm_init(self, id128: bytes):
         buf = C.create_string_buffer(id128, 128)
         _check(lib().dqnb_comm_init(self._h, buf))
+
+    def comm_p2p_handle(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        _check(lib().dqnb_comm_p2p_handle(self._h, buf))
+        return buf.raw
+
+    def comm_p2p_init(self, handles: bytes):
+        buf = C.create_string_buffer(handles, len(handles))
+        _check(lib().dqnb_comm_p2p_init(self._h, buf))
+
+    def comm_status(self) -> int:
+        return int(lib().dqnb_comm_status(self._h))
 
     def sync(self):
         _check(lib().dqnb_sync(self._h))

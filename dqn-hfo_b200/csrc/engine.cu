@@ -211,7 +211,7 @@ struct SplitMat {           // [2][rows][ld] fp32 in HBM
 
 struct Op {                 // one kernel launch of the update / act sequence
   enum Kind { GEMM, GATHER, SAMPLE, HEAD_FWD, CRITIC_HEAD, ACTOR_HEAD_BWD, HEAD_BWD_W, COLSUM, REDUCE,
-              ALLREDUCE, ADAM, PREP, FINALIZE, FORK, JOIN } kind;
+              ALLREDUCE, P2P_ALLREDUCE, ADAM, PREP, FINALIZE, FORK, JOIN } kind;
   int branch = 0;           // 0 = main stream; 1, 2 = side streams between FORK and JOIN
   int wait_ev = -1;         // event the op's stream waits for before the launch (cross-branch edge)
   int rec_ev = -1;          // event recorded on the op's stream after the launch
@@ -219,7 +219,7 @@ struct Op {                 // one kernel launch of the update / act sequence
   int variant = 0;          // 0: always; 1: only when indices are drawn on the device; 2: only when injected
   GemmArgs gemm; dim3 grid;
   GatherArgs gather; HeadArgs head; CriticHeadArgs ch; ActorHeadBwdArgs ahb; HeadBwdWArgs hbw; ColsumArgs cs;
-  ReduceArgs red; AdamArgs adam;
+  ReduceArgs red; AdamArgs adam; P2PArgs p2p;
   float *ar_buf = nullptr; size_t ar_count = 0;
   int blocks = 0;
 };
@@ -242,7 +242,14 @@ struct dqnb_handle_s {
   // params: [2][flat]
   float *P[4] = {nullptr, nullptr, nullptr, nullptr};
   float *Mo[2] = {nullptr, nullptr}, *Vo[2] = {nullptr, nullptr};
-  float *G[2] = {nullptr, nullptr};   // reduced gradients [flat + 4]
+  float *G[2] = {nullptr, nullptr};   // this rank's gradients [flat + 4] (sum of the split-K planes)
+  float *Gr[2] = {nullptr, nullptr};  // gradient the optimiser consumes: G, or the all-reduced copy (P2P exchange)
+  float *xchg = nullptr; long long xchg_floats = 0;   // IPC-exportable exchange allocation (world_size > 1)
+  long long x_in[2] = {0, 0}, x_out[2] = {0, 0}, x_flag = 0;
+  P2PTable *p2p_tab = nullptr; unsigned int *p2p_epoch = nullptr, *p2p_ticket = nullptr; int *p2p_err = nullptr;
+  float *p2p_block_ss = nullptr;
+  std::vector<void *> ipc_opened;
+  int comm_mode = 0;                  // 0 none, 1 NCCL all-reduce, 2 P2P exchange kernel
   float *Gpart[2] = {nullptr, nullptr}; long long gpart_stride[2] = {0, 0};   // [actor, critic]
   float *norm_part = nullptr; int n_norm[2] = {0, 0};
   double *scal_part = nullptr; int n_scal = 0;
@@ -458,6 +465,7 @@ static int launch_op(dqnb_handle_s *h, const Op &op, cudaStream_t s) {
     case Op::HEAD_BWD_W: e = launch_k(head_bwd_w_kernel, op.grid, dim3(256), 0, s, op.hbw); break;
     case Op::COLSUM: e = launch_k(colsum_kernel, op.grid, dim3(1024), 0, s, op.cs); break;
     case Op::REDUCE: e = launch_k(reduce_kernel, dim3(op.blocks), dim3(256), 0, s, op.red); break;
+    case Op::P2P_ALLREDUCE: e = launch_k(p2p_allreduce_kernel, dim3(op.blocks), dim3(512), 0, s, op.p2p); break;
     case Op::ADAM: e = launch_k(adam_kernel, dim3(op.blocks), dim3(256), 0, s, op.adam); break;
     case Op::PREP: e = launch_k(prep_kernel, dim3(1), dim3(32), 0, s, h->st, h->hp); break;
     case Op::FINALIZE:
@@ -598,17 +606,32 @@ static void build_solver(dqnb_handle_s *h, int is_critic, const SegTable &segs, 
   ops.push_back(r);
   if (multi) {
     Op ar;
-    ar.kind = Op::ALLREDUCE; ar.ar_buf = h->G[is_critic]; ar.ar_count = (size_t)g.flat + 4;
-    ops.push_back(ar);
-    Op r2 = r;
-    r2.red.do_reduce = 0; r2.red.do_sumsq = 1;
-    ops.push_back(r2);
+    if (h->comm_mode == 2) {        // fused reduce-scatter + all-gather over NVLink peer memory
+      ar.kind = Op::P2P_ALLREDUCE;
+      P2PArgs &x = ar.p2p;
+      memset(&x, 0, sizeof(x));
+      x.tab = h->p2p_tab; x.world = h->cfg.world_size; x.rank = h->cfg.rank; x.net = is_critic;
+      x.in_off = h->x_in[is_critic]; x.out_off = h->x_out[is_critic]; x.flag_off = h->x_flag;
+      x.count = g.flat + 4; x.epoch = h->p2p_epoch; x.ticket = h->p2p_ticket; x.err = h->p2p_err;
+      x.block_ss = h->p2p_block_ss;
+      ar.blocks = 128;
+      ops.push_back(ar);            // also delivers every rank's share of ||g||^2: no separate norm pass
+    } else {                        // NCCL (validation alternative); launch fails loudly if no communicator
+      ar.kind = Op::ALLREDUCE; ar.ar_buf = h->G[is_critic]; ar.ar_count = (size_t)g.flat + 4;
+      ops.push_back(ar);
+      Op r2 = r;
+      r2.red.do_reduce = 0; r2.red.do_sumsq = 1; r2.red.G = h->Gr[is_critic];
+      ops.push_back(r2);
+    }
   }
   Op ad;
   ad.kind = Op::ADAM;
   AdamArgs &d = ad.adam;
   memset(&d, 0, sizeof(d));
-  d.flat = g.flat; d.G = h->G[is_critic]; d.norm_part = h->norm_part; d.n_norm = blocks;
+  d.flat = g.flat; d.G = h->Gr[is_critic]; d.norm_part = h->norm_part; d.n_norm = blocks;
+  if (multi && h->comm_mode == 2) {   // per-rank slice norms delivered by the exchange kernel
+    d.norm_part = h->xchg + h->x_flag + 4 * kMaxPeers + is_critic * kMaxPeers; d.n_norm = h->cfg.world_size;
+  }
   d.M = h->Mo[is_critic]; d.V = h->Vo[is_critic];
   d.P = h->P[is_critic ? DQNB_CRITIC : DQNB_ACTOR]; d.p_plane = g.flat;
   d.T = h->P[is_critic ? DQNB_CRITIC_TARGET : DQNB_ACTOR_TARGET]; d.t_plane = g.flat;
@@ -721,7 +744,7 @@ static int build_update_ops(dqnb_handle_s *h) {
   build_solver(h, 0, h->segs[0], h->hp.inv_batch_global, ops);
   {   // the last optimiser launch also publishes (critic_loss, avg_q) and advances the counters
     AdamArgs &d = ops.back().adam;
-    d.finalize = 1; d.ticket = h->ticket; d.g_critic_tail = h->G[1] + gC.flat; d.g_actor_tail = h->G[0] + gA.flat;
+    d.finalize = 1; d.ticket = h->ticket; d.g_critic_tail = h->Gr[1] + gC.flat; d.g_actor_tail = h->Gr[0] + gA.flat;
     d.results = h->results; d.max_slots = h->max_slots;
   }
   return 0;
@@ -772,6 +795,7 @@ int dqnb_destroy(dqnb_handle h) {
   if (h->graph_sampled) cudaGraphExecDestroy(h->graph_sampled);
   if (h->graph_injected) cudaGraphExecDestroy(h->graph_injected);
   if (h->comm && nccl().CommDestroy) nccl().CommDestroy(h->comm);
+  for (void *p : h->ipc_opened) cudaIpcCloseMemHandle(p);
   for (void *p : h->allocs) cudaFree(p);
   for (void *p : h->pinned) cudaFreeHost(p);
   for (int b = 0; b < 2; ++b) {
@@ -828,7 +852,20 @@ static int create_impl(const dqnb_config *cfg, dqnb_handle_s *h) {
   const long long fA = h->gA.flat, fC = h->gC.flat, fmax = std::max(fA, fC);
   for (int n = 0; n < 4; ++n) if (dalloc(h, &h->P[n], (size_t)2 * ((n & 1) ? fC : fA))) return -1;
   if (dalloc(h, &h->Mo[0], fA) || dalloc(h, &h->Vo[0], fA) || dalloc(h, &h->Mo[1], fC) || dalloc(h, &h->Vo[1], fC)) return -1;
-  if (dalloc(h, &h->G[0], fA + 4) || dalloc(h, &h->G[1], fC + 4)) return -1;
+  if (c.world_size > 1) {
+    // gradients live in one plain cudaMalloc allocation so that it can be exported with CUDA IPC:
+    // [in actor][in critic][out actor][out critic][flags]
+    h->x_in[0] = 0; h->x_in[1] = fA + 4; h->x_out[0] = h->x_in[1] + fC + 4; h->x_out[1] = h->x_out[0] + fA + 4;
+    h->x_flag = h->x_out[1] + fC + 4;
+    h->xchg_floats = h->x_flag + 256;
+    if (dalloc(h, &h->xchg, (size_t)h->xchg_floats)) return -1;
+    for (int n = 0; n < 2; ++n) { h->G[n] = h->xchg + h->x_in[n]; h->Gr[n] = h->G[n]; }
+    if (dalloc(h, &h->p2p_tab, 1) || dalloc(h, &h->p2p_epoch, 2) || dalloc(h, &h->p2p_ticket, 2) || dalloc(h, &h->p2p_err, 1) ||
+        dalloc(h, &h->p2p_block_ss, 2 * 256)) return -1;
+  } else {
+    if (dalloc(h, &h->G[0], fA + 4) || dalloc(h, &h->G[1], fC + 4)) return -1;
+    h->Gr[0] = h->G[0]; h->Gr[1] = h->G[1];
+  }
   h->gpart_stride[0] = fA; h->gpart_stride[1] = fC;
   if (dalloc(h, &h->Gpart[0], (size_t)kGradSplits * fA) || dalloc(h, &h->Gpart[1], (size_t)kGradSplits * fC)) return -1;
   if (dalloc(h, &h->norm_part, (size_t)(fmax / 1024))) return -1;
@@ -1289,6 +1326,20 @@ int dqnb_evaluate(dqnb_handle h, int32_t n, const float *states, const float *ac
 }
 
 // ----------------------------------- multi-GPU -------------------------------------------------
+}  // extern "C"
+// choosing how gradients are exchanged changes the kernel sequence: rebuild it and drop captured graphs
+static int set_comm_mode(dqnb_handle h, int mode) {
+  DQNB_CUDA(cudaStreamSynchronize(h->stream));
+  h->comm_mode = mode;
+  if (mode != 2) for (int n = 0; n < 2; ++n) h->Gr[n] = h->G[n];
+  if (h->graph_sampled) { cudaGraphExecDestroy(h->graph_sampled); h->graph_sampled = nullptr; }
+  if (h->graph_injected) { cudaGraphExecDestroy(h->graph_injected); h->graph_injected = nullptr; }
+  if (build_update_ops(h)) return -1;
+  if (h->trace) for (int i = 0; i < (int)h->update_ops.size() && i < h->trace_ops; ++i)
+    if (h->update_ops[i].kind == Op::GEMM) h->update_ops[i].gemm.p.dbg_clk = h->trace + 8 * i;
+  return 0;
+}
+extern "C" {
 int dqnb_comm_unique_id(void *id128) {
   if (!id128) DQNB_FAIL("null argument");
   if (!nccl().lib || !nccl().GetUniqueId) DQNB_FAIL("libnccl.so.2 not loadable: %s", dlerror());
@@ -1305,7 +1356,52 @@ int dqnb_comm_init(dqnb_handle h, const void *id128) {
   memcpy(&id, id128, sizeof(id));
   int r = nccl().CommInitRank(&h->comm, h->cfg.world_size, id, h->cfg.rank);
   if (r != 0) DQNB_FAIL("ncclCommInitRank failed: %s", nccl().GetErrorString ? nccl().GetErrorString(r) : "?");
+  return set_comm_mode(h, 1);
+}
+
+// P2P exchange: every rank exports its exchange allocation (64-byte cudaIpcMemHandle) ...
+int dqnb_comm_p2p_handle(dqnb_handle h, void *handle64) {
+  if (!h || !handle64) DQNB_FAIL("bad argument");
+  if (h->cfg.world_size < 2 || !h->xchg) DQNB_FAIL("P2P exchange needs world_size > 1");
+  DQNB_CUDA(cudaSetDevice(h->cfg.device));
+  cudaIpcMemHandle_t mh;
+  DQNB_CUDA(cudaIpcGetMemHandle(&mh, h->xchg));
+  static_assert(sizeof(mh) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(handle64, &mh, 64);
   return 0;
+}
+
+// ... and maps everybody else's (handles: world_size x 64 bytes, in rank order)
+int dqnb_comm_p2p_init(dqnb_handle h, const void *handles) {
+  if (!h || !handles) DQNB_FAIL("bad argument");
+  const int W = h->cfg.world_size;
+  if (W < 2 || W > kMaxPeers || !h->xchg) DQNB_FAIL("P2P exchange supports 2..%d ranks", kMaxPeers);
+  DQNB_CUDA(cudaSetDevice(h->cfg.device));
+  P2PTable tab;
+  memset(&tab, 0, sizeof(tab));
+  for (int p = 0; p < W; ++p) {
+    if (p == h->cfg.rank) { tab.base[p] = h->xchg; continue; }
+    cudaIpcMemHandle_t mh;
+    memcpy(&mh, (const char *)handles + 64 * p, 64);
+    void *ptr = nullptr;
+    DQNB_CUDA(cudaIpcOpenMemHandle(&ptr, mh, cudaIpcMemLazyEnablePeerAccess));
+    h->ipc_opened.push_back(ptr);
+    tab.base[p] = (float *)ptr;
+  }
+  DQNB_CUDA(cudaMemcpy(h->p2p_tab, &tab, sizeof(tab), cudaMemcpyHostToDevice));
+  for (int n = 0; n < 2; ++n) h->Gr[n] = h->xchg + h->x_out[n];
+  return set_comm_mode(h, 2);
+}
+
+// 0 = ok; 1 = a peer did not show up within the exchange kernel's timeout (results are invalid)
+int dqnb_comm_status(dqnb_handle h) {
+  if (!h) return -1;
+  if (!h->p2p_err) return 0;
+  int e = 0;
+  cudaSetDevice(h->cfg.device);
+  cudaStreamSynchronize(h->stream);
+  if (cudaMemcpy(&e, h->p2p_err, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  return e;
 }
 
 int dqnb_sync(dqnb_handle h) {
@@ -1359,7 +1455,7 @@ int64_t dqnb_debug_read(dqnb_handle h, const char *name, float *out, int64_t cap
     const NetGeom &g = c ? h->gC : h->gA;
     cnt = g.caffe_count;
     if (capacity < cnt) return -1;
-    if (read_flat(h, g, h->G[c], nullptr, out)) return -1;
+    if (read_flat(h, g, h->Gr[c], nullptr, out)) return -1;
     return cnt;
   } else if (n == "critic_gnorm" || n == "actor_gnorm") {
     StepState s;

@@ -609,6 +609,140 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamArgs a) {
   if (a.finalize) adam_finalize(a);
 }
 
+// -------------------------------------------------------------------------------------------
+// Data-parallel gradient exchange over NVLink peer memory (one process per GPU, buffers mapped with
+// CUDA IPC): reduce-scatter + all-gather in ONE kernel, no NCCL on the path.
+//   A. every rank announces "my local gradient is complete" by storing the epoch into each peer's flag
+//   B. rank r owns slice r: it sums that slice over all peers' input buffers in fixed rank order
+//      (remote loads, volatile: peer data must not be served from a stale L1 line) and stores the result
+//      into every peer's output buffer (remote stores) -> all replicas receive bit-identical values
+//   C. the last block of every rank signals "my slice is delivered" to all peers and waits for theirs;
+//      when the kernel retires, the whole reduced gradient is in this rank's output buffer.
+// Epochs are device-resident and advance once per call, so the kernel is CUDA-graph replayable.  Every
+// spin has a timeout (err flag) so that a missing peer cannot wedge the GPU.
+constexpr int kMaxPeers = 8;
+struct P2PTable {                 // device-resident, filled by dqnb_comm_p2p_init
+  float *base[kMaxPeers];         // peer exchange allocations (IPC-mapped); base[rank] is our own
+};
+struct P2PArgs {
+  const P2PTable *tab;
+  int world, rank, net;
+  long long in_off, out_off;      // float offsets of this net's input / output buffer inside an exchange allocation
+  long long flag_off;             // float offset of the flag area: uint32 flagA[2][8], flagB[2][8], float norm[2][8]
+  float *block_ss;                // [2][gridDim] local scratch: per-block sum of squares of this rank's slice
+  long long count;                // floats to reduce (multiple of 4)
+  unsigned int *epoch;            // [2] per net, local memory
+  unsigned int *ticket;           // [2] per net, local memory
+  int *err;
+};
+__device__ __forceinline__ unsigned int ld_acquire_sys_u32(const unsigned int *p) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys_u32(unsigned int *p, unsigned int v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ float4 ld_volatile_f4(const float *p) {
+  float4 v;
+  asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ bool spin_until_ge(const unsigned int *flag, unsigned int target, int *err) {
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+  while (ld_acquire_sys_u32(flag) < target) {
+    unsigned long long t1;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+    if (t1 - t0 > 2000000000ull) { *err = 1; return false; }   // 2 s: a peer is gone; give up instead of hanging
+    __nanosleep(64);
+  }
+  return true;
+}
+__global__ void __launch_bounds__(512) p2p_allreduce_kernel(const P2PArgs a) {
+  DQNB_PDL_PROLOGUE();
+  __shared__ int s_last;
+  const int W = a.world;
+  const unsigned int e = a.epoch[a.net] + 1u;
+  float *mine = a.tab->base[a.rank];
+  unsigned int *my_flags = reinterpret_cast<unsigned int *>(mine + a.flag_off);
+  unsigned int *my_flagA = my_flags + a.net * kMaxPeers, *my_flagB = my_flags + 2 * kMaxPeers + a.net * kMaxPeers;
+  // A
+  if (blockIdx.x == 0 && threadIdx.x < W) {
+    __threadfence_system();
+    unsigned int *pf = reinterpret_cast<unsigned int *>(a.tab->base[threadIdx.x] + a.flag_off) + a.net * kMaxPeers;
+    st_release_sys_u32(pf + a.rank, e);
+  }
+  if (threadIdx.x < W) spin_until_ge(my_flagA + threadIdx.x, e, a.err);
+  __syncthreads();
+  // B
+  const long long n4 = a.count / 4, per = (n4 + W - 1) / W;
+  const long long lo = (long long)a.rank * per, hi = min(n4, lo + per);
+  float ss = 0.f;                    // sum of squares of the reduced slice (ClipGradients numerator)
+  const long long n4_real = (a.count - 4) / 4;   // the 4-float tail carries loss / avg-q, not a gradient
+  // The exchange is latency-bound (a few hundred KB per rank over NVLink): each thread first issues every
+  // remote load of a batch of kU float4 elements (kU x world loads in flight), then sums in rank order.
+  constexpr int kU = 2;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i0 = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < hi; i0 += kU * stride) {
+    float4 v[kU][kMaxPeers];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const long long i = i0 + u * stride;
+#pragma unroll
+      for (int p = 0; p < kMaxPeers; ++p)
+        if (p < W && i < hi) v[u][p] = ld_volatile_f4(a.tab->base[p] + a.in_off + 4 * i);
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const long long i = i0 + u * stride;
+      if (i >= hi) continue;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int p = 0; p < kMaxPeers; ++p)
+        if (p < W) { acc.x += v[u][p].x; acc.y += v[u][p].y; acc.z += v[u][p].z; acc.w += v[u][p].w; }
+#pragma unroll
+      for (int p = 0; p < kMaxPeers; ++p)
+        if (p < W) *reinterpret_cast<float4 *>(a.tab->base[p] + a.out_off + 4 * i) = acc;
+      if (i < n4_real) ss += acc.x * acc.x + acc.y * acc.y + acc.z * acc.z + acc.w * acc.w;
+    }
+  }
+  {
+    __shared__ float red[16];
+    ss = warp_sum(ss);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float s = 0.f;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
+      a.block_ss[a.net * gridDim.x + blockIdx.x] = s;
+    }
+  }
+  // C
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(a.ticket + a.net, 1u);
+    s_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (threadIdx.x < W) {
+    // this rank's share of ||g||^2, summed over its blocks in fixed order, travels with the completion flag
+    float s = 0.f;
+    for (int b = 0; b < (int)gridDim.x; ++b) s += reinterpret_cast<volatile float *>(a.block_ss)[a.net * gridDim.x + b];
+    float *pn = a.tab->base[threadIdx.x] + a.flag_off + 4 * kMaxPeers + a.net * kMaxPeers;
+    reinterpret_cast<volatile float *>(pn)[a.rank] = s;
+    __threadfence_system();
+    unsigned int *pf = reinterpret_cast<unsigned int *>(a.tab->base[threadIdx.x] + a.flag_off) + 2 * kMaxPeers + a.net * kMaxPeers;
+    st_release_sys_u32(pf + a.rank, e);
+    spin_until_ge(my_flagB + threadIdx.x, e, a.err);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) { a.ticket[a.net] = 0; a.epoch[a.net] = e; __threadfence(); }
+}
+
 // split an fp32 array into (hi, lo) planes / join it back (parameter import / export)
 __global__ void split_kernel(const float *x, float *hi, float *lo, long long n) {
   DQNB_PDL_PROLOGUE();

@@ -142,6 +142,14 @@ int dqnb_evaluate(dqnb_handle h, int32_t n, const float *states, const float *ac
  * id128 is an ncclUniqueId obtained on rank 0 and broadcast by the caller. */
 int dqnb_comm_unique_id(void *id128);
 int dqnb_comm_init(dqnb_handle h, const void *id128);
+/* Product path for the gradient exchange: a fused reduce-scatter + all-gather kernel over NVLink peer
+ * memory (csrc/kernels.cuh p2p_allreduce_kernel), no NCCL.  Every rank exports the 64-byte CUDA-IPC handle
+ * of its exchange buffer, the caller gathers the world_size handles in rank order (any transport) and
+ * every rank maps them.  Selecting either exchange rebuilds the captured update graph. */
+int dqnb_comm_p2p_handle(dqnb_handle h, void *handle64);
+int dqnb_comm_p2p_init(dqnb_handle h, const void *handles /* world_size x 64 bytes */);
+/* 0 = healthy; 1 = a peer missed the exchange kernel's 2 s timeout (state is no longer valid). */
+int dqnb_comm_status(dqnb_handle h);
 
 /* Blocks until all work queued on the handle has finished. */
 int dqnb_sync(dqnb_handle h);
