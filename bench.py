@@ -188,7 +188,8 @@ def run_reference(args):
         "impl": "reference", "metric": "transition-updates/sec", "value": val, "unit": "transitions/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, 1),
+        "config": dict(workload_config(args, 1), precision="fp32 on the host cores (CPU port of the reference's Caffe operation order)",
+                       parallelism=f"{cores} host threads"),
         "cpu_baseline": {"value": val, "unit": "transitions/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "transitions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
