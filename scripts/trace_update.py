@@ -21,7 +21,7 @@ d.update(1)
 buf = (C.c_longlong * 4096)()
 n = L.dqnb_debug_trace(d._h, buf, 4096)
 t = np.array(list(buf[:n]), dtype=np.int64).reshape(-1, 8)
-kinds = ["GEMM","GATHER","SAMPLE","HEAD_FWD","CRITIC_HEAD","ACTOR_HEAD_BWD","HEAD_BWD_W","COLSUM","REDUCE","ALLREDUCE","ADAM","PREP","FINALIZE","FORK","JOIN"]
+kinds = ["GEMM","GATHER","SAMPLE","HEAD_FWD","CRITIC_HEAD","ACTOR_HEAD_BWD","HEAD_BWD_W","COLSUM","REDUCE","ALLREDUCE","P2P_ALLREDUCE","ADAM","PREP","FINALIZE","FORK","JOIN"]
 g = [i for i in range(len(t)) if t[i,7]//1000 == 0]
 t0 = min(t[i,0] for i in g)
 print(" op kind        br grid(x,y,z) kb |  entry  pdlwait  operands acc_done epi_done | dur(after wait)")
