@@ -210,7 +210,7 @@ struct SplitMat {           // [2][rows][ld] fp32 in HBM
 };
 
 struct Op {                 // one kernel launch of the update / act sequence
-  enum Kind { GEMM, GATHER, SAMPLE, HEAD_FWD, CRITIC_HEAD, ACTOR_HEAD_BWD, HEAD_BWD_W, COLSUM, REDUCE,
+  enum Kind { GEMM, GEMM_GROUP, GATHER, SAMPLE, HEAD_FWD, CRITIC_HEAD, ACTOR_HEAD_BWD, HEAD_BWD_W, COLSUM, REDUCE,
               ALLREDUCE, P2P_ALLREDUCE, ADAM, PREP, FINALIZE, FORK, JOIN } kind;
   int branch = 0;           // 0 = main stream; 1, 2 = side streams between FORK and JOIN
   int wait_ev = -1;         // event the op's stream waits for before the launch (cross-branch edge)
@@ -218,6 +218,7 @@ struct Op {                 // one kernel launch of the update / act sequence
   int mask = 3;             // FORK / JOIN: which side streams take part
   int variant = 0;          // 0: always; 1: only when indices are drawn on the device; 2: only when injected
   GemmArgs gemm; dim3 grid;
+  GroupArgs group;          // GEMM_GROUP: several GEMMs in one launch
   GatherArgs gather; HeadArgs head; CriticHeadArgs ch; ActorHeadBwdArgs ahb; HeadBwdWArgs hbw; ColsumArgs cs;
   ReduceArgs red; AdamArgs adam; P2PArgs p2p;
   float *ar_buf = nullptr; size_t ar_count = 0;
@@ -454,6 +455,9 @@ static int launch_op(dqnb_handle_s *h, const Op &op, cudaStream_t s) {
       else
         e = launch_k(gemm_simt_kernel, op.grid, dim3(256), 0, s, op.gemm.p);
       break;
+    case Op::GEMM_GROUP:
+      e = launch_k(gemm_tc_grouped_kernel<1, 1, 64>, op.grid, dim3(TC_THREADS), (size_t)tc_smem_for(64), s, op.group);
+      break;
     case Op::GATHER: e = launch_k(gather_kernel, dim3(h->Bp), dim3(128), 0, s, op.gather); break;
     case Op::SAMPLE:
       e = launch_k(sample_kernel, dim3((h->B + 255) / 256), dim3(256), 0, s, (const StepState *)h->st,
@@ -547,6 +551,15 @@ static int build_backward(dqnb_handle_s *h, const NetGeom &g, const float *P, co
     Op f; f.kind = Op::FORK; f.mask = 1; ops.push_back(f);    // side 1 joins after head_bwd_x (dZ[top] ready)
     if (head_bwd_w) { Op w = *head_bwd_w; w.branch = 1; ops.push_back(w); }
   }
+  // Experiment kept behind DQNB_GROUPED_DW=1: the weight-gradient GEMMs of all layers as ONE grouped launch
+  // after the dX chain.  Measured 2.75e6 vs 2.75-2.79e6 tr/s for the per-layer launches that overlap the
+  // chain on the side stream (the group is ~3 waves of CTAs that only start when the chain is done).
+  const bool grouped = want_dw && h->cfg.gemm_mode == DQNB_GEMM_TCGEN05_3XTF32 && g.n_hidden <= kMaxGroup &&
+                       getenv("DQNB_GROUPED_DW") != nullptr;
+  Op grp;
+  grp.kind = Op::GEMM_GROUP;
+  grp.group.n = 0;
+  grp.group.tile_begin[0] = 0;
   for (int l = top; l >= 0; --l) {
     if (want_dw) {
       Op op;
@@ -554,7 +567,13 @@ static int build_backward(dqnb_handle_s *h, const NetGeom &g, const float *P, co
       if (op_dw(h->cfg, g, l, h->dZ[l], l > 0 ? acts[l - 1] : X, h->Gpart[g.critic], h->gpart_stride[g.critic], &splits, &op)) return -1;
       op.branch = 1;
       if (l < top) op.wait_ev = l;                              // dZ[l] is produced by the dX op below
-      ops.push_back(op);
+      if (grouped) {
+        const int i = grp.group.n++;
+        grp.group.g[i] = op.gemm;
+        grp.group.tile_begin[i + 1] = grp.group.tile_begin[i] + (int)(op.grid.x * op.grid.y * op.grid.z);
+      } else {
+        ops.push_back(op);
+      }
       // segment table entries (internal flat order: W_l then b_l)
       SegTable &T = *segs;
       T.begin[2 * l] = g.L[l].w_off; T.end[2 * l] = g.L[l].b_off; T.nsplit[2 * l] = splits;
@@ -566,6 +585,12 @@ static int build_backward(dqnb_handle_s *h, const NetGeom &g, const float *P, co
       if (want_dw) op.rec_ev = l - 1;                           // dZ[l-1] ready
       ops.push_back(op);
     }
+  }
+  if (grouped) {
+    grp.branch = 1;
+    if (g.n_hidden > 1) grp.wait_ev = 0;                        // dZ[0] is the last one the chain produces
+    grp.grid = dim3(grp.group.tile_begin[grp.group.n]);
+    ops.push_back(grp);
   }
   if (want_dw) {
     Op op;
@@ -1240,12 +1265,12 @@ int dqnb_benchmark_gemms(dqnb_handle h, int32_t reps, float *ms_per_update, int3
   if (!h || reps <= 0 || !ms_per_update) DQNB_FAIL("bad argument");
   DQNB_CUDA(cudaSetDevice(h->cfg.device));
   int n = 0;
-  for (const Op &op : h->update_ops) if (op.kind == Op::GEMM) ++n;
+  for (const Op &op : h->update_ops) if (op.kind == Op::GEMM || op.kind == Op::GEMM_GROUP) ++n;
   DQNB_CUDA(cudaStreamSynchronize(h->stream));
   for (int r = 0; r < reps + 2; ++r) {
     if (r == 2) DQNB_CUDA(cudaEventRecord(h->ev0, h->stream));
     for (const Op &op : h->update_ops)
-      if (op.kind == Op::GEMM && launch_op(h, op, h->stream)) return -1;
+      if ((op.kind == Op::GEMM || op.kind == Op::GEMM_GROUP) && launch_op(h, op, h->stream)) return -1;
   }
   DQNB_CUDA(cudaEventRecord(h->ev1, h->stream));
   DQNB_CUDA(cudaEventSynchronize(h->ev1));

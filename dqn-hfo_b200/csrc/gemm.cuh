@@ -302,7 +302,7 @@ __device__ __forceinline__ float4 ld_dsmem_f4(uint32_t local_saddr, uint32_t ran
 // issues.  A single divergent thread doing that arithmetic costs ~300 cycles per k-step, 3x the
 // tensor time of the three MMAs it feeds (measured: profiles/r01_gemm_issue_loop.md).
 template <int A_MN, int B_MN, int BN_>
-__global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmArgs args) {
+__device__ __forceinline__ void gemm_tc_body(const GemmArgs &args, const int n_tile, const int m_tile, const int split) {
   using Cfg = TcCfg<BN_>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -314,7 +314,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
   volatile uint32_t *tmem_slot =
       reinterpret_cast<volatile uint32_t *>(base_ptr + STAGES * Cfg::STAGE_BYTES + 128);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_tile = blockIdx.x, m_tile = blockIdx.y, split = blockIdx.z;
   const int kblocks = p.K / BK;
   const int per = (kblocks + p.splits - 1) / p.splits;
   const int kb0 = split * per;
@@ -600,6 +599,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
   }
 }
 
+template <int A_MN, int B_MN, int BN_>
+__global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmArgs args) {
+  gemm_tc_body<A_MN, B_MN, BN_>(args, blockIdx.x, blockIdx.y, blockIdx.z);
+}
+
+// Grouped launch: several independent GEMMs (the four weight-gradient GEMMs of one backward pass) share one
+// grid, so they cost one launch and fill the machine together.  blockIdx.x enumerates the tiles of all
+// members; the tensor maps stay in the (grid-constant) parameter space.
+constexpr int kMaxGroup = 4;
+struct alignas(64) GroupArgs {
+  GemmArgs g[kMaxGroup];
+  int n;
+  int tile_begin[kMaxGroup + 1];
+};
+template <int A_MN, int B_MN, int BN_>
+__global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_grouped_kernel(const __grid_constant__ GroupArgs ga) {
+  int i = 0;
+  const int t = blockIdx.x;
+  while (i + 1 < ga.n && t >= ga.tile_begin[i + 1]) ++i;
+  const GemmArgs &args = ga.g[i];
+  const int local = t - ga.tile_begin[i];
+  const int nt = (args.p.N + BN_ - 1) / BN_, mt = (args.p.M + BM - 1) / BM;
+  gemm_tc_body<A_MN, B_MN, BN_>(args, local % nt, (local / nt) % mt, local / (nt * mt));
+}
+
 // host-side dispatch over the template instances
 typedef void (*TcKernel)(const GemmArgs);
 inline TcKernel tc_kernel_for(int a_mn, int b_mn, int bn) {
@@ -616,6 +640,11 @@ inline TcKernel tc_kernel_for(int a_mn, int b_mn, int bn) {
 }
 inline int tc_smem_for(int bn) { return bn == 128 ? TcCfg<128>::SMEM_BYTES : TcCfg<64>::SMEM_BYTES; }
 inline cudaError_t tc_prepare_all() {
+  {
+    cudaError_t e = cudaFuncSetAttribute((const void *)gemm_tc_grouped_kernel<1, 1, 64>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_for(64));
+    if (e != cudaSuccess) return e;
+  }
   for (int bn : {64, 128})
     for (int a = 0; a < 2; ++a)
       for (int b = 0; b < 2; ++b) {
