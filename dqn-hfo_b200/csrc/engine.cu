@@ -548,8 +548,10 @@ static int build_backward(dqnb_handle_s *h, const NetGeom &g, const float *P, co
   const int top = g.n_hidden - 1;
   if (g.n_hidden + 1 > 8) DQNB_FAIL("too many layers for the event table");
   if (want_dw) {
-    Op f; f.kind = Op::FORK; f.mask = 1; ops.push_back(f);    // side 1 joins after head_bwd_x (dZ[top] ready)
-    if (head_bwd_w) { Op w = *head_bwd_w; w.branch = 1; ops.push_back(w); }
+    // both side streams pick up once dZ[top] exists: side 1 runs the per-layer weight-gradient GEMMs, side 2
+    // the head weight/bias gradient, so neither delays the other
+    Op f; f.kind = Op::FORK; f.mask = 3; ops.push_back(f);
+    if (head_bwd_w) { Op w = *head_bwd_w; w.branch = 2; ops.push_back(w); }
   }
   // Experiment kept behind DQNB_GROUPED_DW=1: the weight-gradient GEMMs of all layers as ONE grouped launch
   // after the dX chain.  Measured 2.75e6 vs 2.75-2.79e6 tr/s for the per-layer launches that overlap the
@@ -611,7 +613,7 @@ static int build_backward(dqnb_handle_s *h, const NetGeom &g, const float *P, co
     const int hs = 2 * g.n_hidden;
     T.begin[hs] = g.hw_off; T.end[hs] = g.flat; T.nsplit[hs] = kGradSplits;   // head W, b (+ zero tail)
     T.n = hs + 1;
-    Op j; j.kind = Op::JOIN; j.mask = 1; ops.push_back(j);
+    Op j; j.kind = Op::JOIN; j.mask = 3; ops.push_back(j);
   }
   return 0;
 }
