@@ -205,6 +205,7 @@ static void internal_to_caffe(const NetGeom &g, const float *in, float *c) {
 // ---------------------------------------------------------------------------------------------
 struct SplitMat {           // [2][rows][ld] fp32 in HBM
   float *p = nullptr;
+  uint32_t *bits = nullptr; // optional [rows][ld/32]: ReLU sign bits of a saved activation (gemm.cuh relu_bits_*)
   int rows = 0, ld = 0;
   long long plane() const { return (long long)rows * ld; }
 };
@@ -308,9 +309,39 @@ static int halloc(dqnb_handle_s *h, T **p, size_t count) {
   *p = (T *)d;
   return 0;
 }
-static int alloc_mat(dqnb_handle_s *h, SplitMat *m, int rows, int ld) {
+static int alloc_mat(dqnb_handle_s *h, SplitMat *m, int rows, int ld, bool with_bits = false) {
   m->rows = rows; m->ld = ld;
+  if (with_bits && dalloc(h, &m->bits, (size_t)rows * (ld / 32))) return -1;
   return dalloc(h, &m->p, (size_t)2 * rows * ld);
+}
+
+// ---------------------------------------------------------------------------------------------
+// schedule / tile-shape knobs.  Defaults are the measured best (profiles/r01c_sched_sweep.txt); every knob
+// can be overridden through the environment for experiments (scripts/sweep_sched.py).
+// ---------------------------------------------------------------------------------------------
+static int env_int(const char *name, int dflt) {
+  const char *v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
+struct Tuning {
+  int sched;        // 0: three forward chains at once; 1: (target actor || critic) then (target critic || actor)
+  int dw0_main;     // 1: the last weight-gradient GEMM (layer 0) follows the dX chain on the main stream
+  int colsum_side;  // 1: bias column sums on side stream 1 beside that GEMM
+  int bn_fwd, bn_fwd_side, bn_dx, bn_dw;   // N tile (64 / 128) per GEMM class
+  Tuning() {
+    sched = env_int("DQNB_SCHED", 0);
+    dw0_main = env_int("DQNB_DW0_MAIN", 0);
+    colsum_side = env_int("DQNB_COLSUM_SIDE", 0);
+    bn_fwd = env_int("DQNB_BN_FWD", 64);
+    bn_fwd_side = env_int("DQNB_BN_FWD_SIDE", 64);
+    bn_dx = env_int("DQNB_BN_DX", 64);
+    bn_dw = env_int("DQNB_BN_DW", 64);
+  }
+};
+static const Tuning &tuning() {
+  static thread_local Tuning t;
+  t = Tuning();           // re-read: the sweep script changes the environment between handles
+  return t;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -329,6 +360,7 @@ static int finish_gemm(const dqnb_config &cfg, Op *op) {
     // A
     const int a_rows = p.a_mn ? p.K : p.M, b_rows = p.b_mn ? p.K : p.N;
     if (p.bn != 64 && p.bn != 128) p.bn = 64;
+    if (p.epi == EPI_DX && !p.relu_bits_in) DQNB_FAIL("EPI_DX needs the sign bits of the saved activation");
     // Forward / dX GEMMs with a long contraction but few output tiles: split K over a 2-CTA cluster
     // (DSMEM reduction in the epilogue) so that the dependent chain sees half the mainloop latency.
     {
@@ -350,15 +382,17 @@ static int finish_gemm(const dqnb_config &cfg, Op *op) {
 
 // forward of tower layer l: H = lrelu(X W^T + b)
 static int op_fwd(const dqnb_config &cfg, const NetGeom &g, int l, const float *P, const SplitMat &X,
-                  const SplitMat &H, Op *op) {
+                  const SplitMat &H, Op *op, int bn = 64) {
   const LayerGeom &L = g.L[l];
   GemmParams &p = op->gemm.p;
   memset(&p, 0, sizeof(p));
+  p.bn = (bn == 128 && L.Np % 128 == 0) ? 128 : 64;
   p.M = X.rows; p.N = L.Np; p.K = L.Kp; p.a_mn = 0; p.b_mn = 0; p.splits = 1; p.epi = EPI_FWD;
   p.A = X.p; p.a_plane = X.plane(); p.lda = X.ld;
   p.B = P + L.w_off; p.b_plane = g.flat; p.ldb = L.Kp;
   p.out_hi = H.p; p.out_lo = H.p + H.plane(); p.ldo = H.ld;
   p.bias_hi = P + L.b_off; p.bias_lo = P + g.flat + L.b_off; p.apply_lrelu = 1;
+  p.relu_bits_out = H.bits; p.ldbits = H.ld / 32;
   return finish_gemm(cfg, op);
 }
 // backward w.r.t. bottom of layer l (l >= 1): dZ_{l-1} = (dZ_l W_l) * relu'(H_{l-1})
@@ -367,11 +401,13 @@ static int op_dx(const dqnb_config &cfg, const NetGeom &g, int l, const float *P
   const LayerGeom &L = g.L[l];
   GemmParams &p = op->gemm.p;
   memset(&p, 0, sizeof(p));
+  p.bn = (tuning().bn_dx == 128 && L.Kp % 128 == 0) ? 128 : 64;
   p.M = dZl.rows; p.N = L.Kp; p.K = L.Np; p.a_mn = 0; p.b_mn = 1; p.splits = 1; p.epi = EPI_DX;
   p.A = dZl.p; p.a_plane = dZl.plane(); p.lda = dZl.ld;
   p.B = P + L.w_off; p.b_plane = g.flat; p.ldb = L.Kp;
   p.out_hi = dZprev.p; p.out_lo = dZprev.p + dZprev.plane(); p.ldo = dZprev.ld;
   p.mask_hi = Hprev.p; p.mask_lo = Hprev.p + Hprev.plane(); p.ldmask = Hprev.ld;
+  p.relu_bits_in = Hprev.bits; p.ldbits = Hprev.ld / 32;
   return finish_gemm(cfg, op);
 }
 // input diff of layer 0 (critic policy pass): d_in = dZ_0 W_0, raw fp32
@@ -397,7 +433,8 @@ static int op_dw(const dqnb_config &cfg, const NetGeom &g, int l, const SplitMat
   GemmParams &p = op->gemm.p;
   memset(&p, 0, sizeof(p));
   p.M = L.Np; p.N = L.Kp; p.K = dZl.rows; p.a_mn = 1; p.b_mn = 1; p.epi = EPI_PLAIN;
-  const int tiles = ((p.M + BM - 1) / BM) * ((p.N + 63) / 64);
+  p.bn = (tuning().bn_dw == 128 && L.Kp % 128 == 0) ? 128 : 64;
+  const int tiles = ((p.M + BM - 1) / BM) * ((p.N + p.bn - 1) / p.bn);
   p.splits = pick_splits(tiles, p.K / BK, kGradSplits);
   *splits_out = p.splits;
   p.A = dZl.p; p.a_plane = dZl.plane(); p.lda = dZl.ld;
@@ -526,7 +563,7 @@ static int build_forward(dqnb_handle_s *h, const NetGeom &g, const float *P, con
   const SplitMat *in = &X;
   for (int l = 0; l < g.n_hidden; ++l) {
     Op op;
-    if (op_fwd(h->cfg, g, l, P, *in, acts[l], &op)) return -1;
+    if (op_fwd(h->cfg, g, l, P, *in, acts[l], &op, critical_chain ? tuning().bn_fwd : tuning().bn_fwd_side)) return -1;
     if (!critical_chain && op.gemm.p.cluster_k) {
       // side-branch passes run beside the critical chain: they should not grab twice the SMs for a
       // latency that nobody waits on, so they keep one CTA per tile
@@ -569,6 +606,11 @@ static int build_backward(dqnb_handle_s *h, const NetGeom &g, const float *P, co
       if (op_dw(h->cfg, g, l, h->dZ[l], l > 0 ? acts[l - 1] : X, h->Gpart[g.critic], h->gpart_stride[g.critic], &splits, &op)) return -1;
       op.branch = 1;
       if (l < top) op.wait_ev = l;                              // dZ[l] is produced by the dX op below
+      if (l == 0 && top > 0 && tuning().dw0_main && !grouped) {
+        // the last weight gradient only waits for the dX op right before it: on the main stream it starts with a
+        // programmatic hand-off instead of a cross-stream event (measured ~10 us later)
+        op.branch = 0; op.wait_ev = -1;
+      }
       if (grouped) {
         const int i = grp.group.n++;
         grp.group.g[i] = op.gemm;
@@ -608,6 +650,7 @@ static int build_backward(dqnb_handle_s *h, const NetGeom &g, const float *P, co
     a.blk_begin[g.n_hidden] = blk;
     a.gpart = h->Gpart[g.critic]; a.gpart_stride = h->gpart_stride[g.critic];
     op.grid = dim3(blk, kGradSplits);
+    if (tuning().colsum_side && top > 0) { op.branch = 1; op.wait_ev = 0; }   // beside the layer-0 weight gradient
     ops.push_back(op);
     SegTable &T = *segs;
     const int hs = 2 * g.n_hidden;
@@ -721,25 +764,39 @@ static int build_update_ops(dqnb_handle_s *h) {
   //   main  : dqn.cpp:889-891 CriticForwardThroughActor(critic_target, actor_target, s') + TD target
   //   side 1: forward half of critic_solver_->Step(1) on (s, a, p)            (dqn.cpp:904)
   //   side 2: actor forward on s with the pre-update actor                    (dqn.cpp:910-911)
+  // sched 1: only two chains compete at any time: (target actor || critic), then (target critic || actor).  The
+  // actor chain waits for the target actor's head (event 7) and is joined with the critic's gradient branch,
+  // long before its consumer (the critic forward on (s, a_pi)) runs.
+  const int sched = tuning().sched;
   const int side2 = getenv("DQNB_SIDE_SERIAL") ? 1 : 2;   // measured: three concurrent chains beat two (2.78e6 vs 2.73e6 tr/s)
-  op.kind = Op::FORK; op.mask = side2 == 2 ? 3 : 1; ops.push_back(op);
+  const int fork_mask = sched == 1 ? 1 : (side2 == 2 ? 3 : 1);
+  constexpr int kEvActorStart = 7;
+  op.kind = Op::FORK; op.mask = fork_mask; ops.push_back(op);
   {
     const size_t mark = ops.size();
     if (build_forward(h, gC, PC, h->Xc, h->actC, ops, false)) return -1;
     for (size_t i = mark; i < ops.size(); ++i) ops[i].branch = 1;
   }
-  {
+  auto push_actor_chain = [&](int branch, int wait_ev) -> int {
     const size_t mark = ops.size();
     if (build_forward(h, gA, PA, h->Xs, h->actA, ops, false)) return -1;
-    op_head_fwd(gA, PA, h->actA[topA], h->B, h->a16_pi, &h->Xcp, h->S, &op); ops.push_back(op);
-    for (size_t i = mark; i < ops.size(); ++i) ops[i].branch = side2;   // same side stream: at most two chains compete
-  }
+    Op hd;
+    op_head_fwd(gA, PA, h->actA[topA], h->B, h->a16_pi, &h->Xcp, h->S, &hd); ops.push_back(hd);
+    for (size_t i = mark; i < ops.size(); ++i) ops[i].branch = branch;
+    ops[mark].wait_ev = wait_ev;
+    return 0;
+  };
+  if (sched != 1 && push_actor_chain(side2, -1)) return -1;   // same side stream: at most two chains compete
   op.branch = 0;
   if (build_forward(h, gA, PAT, h->Xsn, h->actAT, ops)) return -1;
-  op_head_fwd(gA, PAT, h->actAT[topA], h->B, h->a16_t, &h->Xct, h->S, &op); ops.push_back(op);
+  op_head_fwd(gA, PAT, h->actAT[topA], h->B, h->a16_t, &h->Xct, h->S, &op);
+  if (sched == 1) op.rec_ev = kEvActorStart;
+  ops.push_back(op);
+  op.rec_ev = -1;
+  if (sched == 1 && push_actor_chain(2, kEvActorStart)) return -1;
   if (build_forward(h, gC, PCT, h->Xct, h->actCT, ops)) return -1;
   push_critic_head(h, QMODE_TARGET, PCT, h->actCT[topC], h->q_next, ops);   // dqn.cpp:892-900
-  op.kind = Op::JOIN; op.mask = side2 == 2 ? 3 : 1; ops.push_back(op);
+  op.kind = Op::JOIN; op.mask = fork_mask; ops.push_back(op);
   // rest of critic_solver_->Step(1): loss, backward, clip, Adam (+ soft update of the target critic)
   push_critic_head(h, QMODE_LOSS, PC, h->actC[topC], h->q, ops);
   Op hbw = make_head_bwd_w(h, gC, h->d16c, h->actC[topC]);
@@ -776,6 +833,28 @@ static int build_update_ops(dqnb_handle_s *h) {
     d.results = h->results; d.max_slots = h->max_slots;
   }
   return 0;
+}
+
+// DQNB_TRACE=1: every op of the update sequence gets an 8-slot timeline record (kernels.cuh trace_begin/end)
+static void attach_trace(dqnb_handle_s *h) {
+  if (!h->trace) return;
+  for (int i = 0; i < (int)h->update_ops.size() && i < h->trace_ops; ++i) {
+    Op &op = h->update_ops[i];
+    long long *t = h->trace + kTraceSlots * i;
+    switch (op.kind) {
+      case Op::GEMM: op.gemm.p.dbg_clk = t; break;
+      case Op::GATHER: op.gather.trace = t; break;
+      case Op::HEAD_FWD: op.head.trace = t; break;
+      case Op::CRITIC_HEAD: op.ch.trace = t; break;
+      case Op::ACTOR_HEAD_BWD: op.ahb.trace = t; break;
+      case Op::HEAD_BWD_W: op.hbw.trace = t; break;
+      case Op::COLSUM: op.cs.trace = t; break;
+      case Op::REDUCE: op.red.trace = t; break;
+      case Op::ADAM: op.adam.trace = t; break;
+      case Op::P2P_ALLREDUCE: op.p2p.trace = t; break;
+      default: break;
+    }
+  }
 }
 
 static int build_act_ops(dqnb_handle_s *h) {
@@ -918,8 +997,8 @@ static int create_impl(const dqnb_config *cfg, dqnb_handle_s *h) {
   if (dalloc(h, &h->d_in, (size_t)kGradSplits * h->Bp * h->Kc) || dalloc(h, &h->tap_raw, (size_t)h->Bp * kActorOut) || dalloc(h, &h->tap_inv, (size_t)h->Bp * kActorOut)) return -1;
   for (int l = 0; l < c.n_hidden; ++l) {
     const int Np = h->gA.L[l].Np;
-    if (alloc_mat(h, &h->actAT[l], h->Bp, Np) || alloc_mat(h, &h->actCT[l], h->Bp, Np) || alloc_mat(h, &h->actC[l], h->Bp, Np) ||
-        alloc_mat(h, &h->actA[l], h->Bp, Np) || alloc_mat(h, &h->dZ[l], h->Bp, Np) || alloc_mat(h, &h->actE[l], h->An, Np)) return -1;
+    if (alloc_mat(h, &h->actAT[l], h->Bp, Np) || alloc_mat(h, &h->actCT[l], h->Bp, Np) || alloc_mat(h, &h->actC[l], h->Bp, Np, true) ||
+        alloc_mat(h, &h->actA[l], h->Bp, Np, true) || alloc_mat(h, &h->dZ[l], h->Bp, Np) || alloc_mat(h, &h->actE[l], h->An, Np)) return -1;
   }
   if (alloc_mat(h, &h->Xact, h->An, h->Sp) || alloc_mat(h, &h->Xeval, h->An, h->Kc)) return -1;
   if (halloc(h, &h->h_act_in, (size_t)2 * h->An * h->Kc) || halloc(h, &h->h_act_out, (size_t)h->An * 16)) return -1;
@@ -936,10 +1015,9 @@ static int create_impl(const dqnb_config *cfg, dqnb_handle_s *h) {
   if (halloc(h, &h->h_stage, (size_t)h->stage_rows * h->rw)) return -1;
   if (build_update_ops(h) || build_act_ops(h)) return -1;
   if (getenv("DQNB_TRACE")) {
-    h->trace_ops = (int)h->update_ops.size();
-    if (dalloc(h, &h->trace, (size_t)8 * h->trace_ops)) return -1;
-    for (int i = 0; i < h->trace_ops; ++i)
-      if (h->update_ops[i].kind == Op::GEMM) h->update_ops[i].gemm.p.dbg_clk = h->trace + 8 * i;
+    h->trace_ops = (int)h->update_ops.size() + 16;   // head room: the op list grows when a communicator is attached
+    if (dalloc(h, &h->trace, (size_t)kTraceSlots * h->trace_ops)) return -1;
+    attach_trace(h);
   }
   DQNB_CUDA(cudaStreamSynchronize(h->stream));
   DQNB_CUDA(cudaDeviceSynchronize());
@@ -1199,6 +1277,7 @@ static int ensure_graph(dqnb_handle h, bool injected) {
 
 static int enqueue_update(dqnb_handle h, bool injected) {
   h->host_step += 1;
+  if (h->trace) DQNB_CUDA(cudaMemsetAsync(h->trace, 0xFF, sizeof(long long) * kTraceSlots * h->trace_ops, h->stream));
   if (h->cfg.use_graph) {
     if (ensure_graph(h, injected)) return -1;
     DQNB_CUDA(cudaGraphLaunch(injected ? h->graph_injected : h->graph_sampled, h->stream));
@@ -1367,8 +1446,7 @@ static int set_comm_mode(dqnb_handle h, int mode) {
   if (h->graph_sampled) { cudaGraphExecDestroy(h->graph_sampled); h->graph_sampled = nullptr; }
   if (h->graph_injected) { cudaGraphExecDestroy(h->graph_injected); h->graph_injected = nullptr; }
   if (build_update_ops(h)) return -1;
-  if (h->trace) for (int i = 0; i < (int)h->update_ops.size() && i < h->trace_ops; ++i)
-    if (h->update_ops[i].kind == Op::GEMM) h->update_ops[i].gemm.p.dbg_clk = h->trace + 8 * i;
+  attach_trace(h);
   return 0;
 }
 extern "C" {
@@ -1445,21 +1523,25 @@ int dqnb_sync(dqnb_handle h) {
 
 int64_t dqnb_kernel_launches(dqnb_handle h) { return h ? h->launches : -1; }
 
-// DQNB_TRACE=1 only: per-op timeline of the last update, 8 int64 per op of the update sequence
+// DQNB_TRACE=1 only: per-op timeline of the last update, kTraceSlots int64 per op of the update sequence
 // ({kind, branch} in slots 7/6 are filled here; slots 0-5 are globaltimer ns stamps of GEMM ops).
 int64_t dqnb_debug_trace(dqnb_handle h, long long *out, int64_t capacity) {
   if (!h || !h->trace || !out) return -1;
-  const int64_t n = (int64_t)8 * h->trace_ops;
+  const int64_t n = (int64_t)kTraceSlots * h->trace_ops;
   if (capacity < n) return -1;
   cudaSetDevice(h->cfg.device);
   cudaStreamSynchronize(h->stream);
   if (cudaMemcpy(out, h->trace, sizeof(long long) * n, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
-  for (int i = 0; i < h->trace_ops; ++i) {
+  const int n_ops = std::min(h->trace_ops, (int)h->update_ops.size());
+  for (int i = 0; i < n_ops; ++i) {
     const Op &op = h->update_ops[i];
-    out[8 * i + 7] = (long long)op.kind * 1000 + op.branch;
-    if (op.kind == Op::GEMM) out[8 * i + 6] = ((long long)op.grid.x << 40) | ((long long)op.grid.y << 20) | op.grid.z | ((long long)(op.gemm.p.K / 32) << 52);
+    long long meta = (long long)op.kind * 1000 + op.branch;          // 16 bits
+    if (op.kind == Op::GEMM)                                         // grid x:12 y:12 z:8, k-blocks:12
+      meta |= ((long long)(op.grid.x & 0xfff) << 16) | ((long long)(op.grid.y & 0xfff) << 28) | ((long long)(op.grid.z & 0xff) << 40) |
+              ((long long)((op.gemm.p.K / 32) & 0xfff) << 48);
+    out[kTraceSlots * i + 7] = meta;
   }
-  return n;
+  return (int64_t)kTraceSlots * n_ops;
 }
 
 int64_t dqnb_debug_read(dqnb_handle h, const char *name, float *out, int64_t capacity) {
@@ -1502,8 +1584,8 @@ int64_t dqnb_debug_read(dqnb_handle h, const char *name, float *out, int64_t cap
 }
 
 // ----------------------------------- kernel unit test ------------------------------------------
-static long long g_dbg_clk[8 * 32];
-void dqnb_gemm_test_clocks(long long *out, int n) { for (int i = 0; i < n && i < 8 * 32; ++i) out[i] = g_dbg_clk[i]; }
+static long long g_dbg_clk[kTraceSlots * 32];
+void dqnb_gemm_test_clocks(long long *out, int n) { for (int i = 0; i < n && i < kTraceSlots * 32; ++i) out[i] = g_dbg_clk[i]; }
 
 int dqnb_gemm_test(int device, int gemm_mode, int a_mn, int b_mn, int M, int N, int K, int splits,
                    const float *A, const float *B, float *C, float *elapsed_ms) {
@@ -1543,7 +1625,7 @@ int dqnb_gemm_test(int device, int gemm_mode, int a_mn, int b_mn, int M, int N, 
   const int reps = 20;
   for (int r = 0; r < 1 + reps; ++r) {
     if (r == 1) DQNB_CUDA(cudaEventRecord(e0, 0));
-    p.dbg_clk = dclk + 8 * r;            // per-launch timeline slot
+    p.dbg_clk = dclk + kTraceSlots * r;            // per-launch timeline slot
     if (gemm_mode == DQNB_GEMM_TCGEN05_3XTF32)
       DQNB_CUDA(launch_k(tc_kernel_for(a_mn, b_mn, p.bn), op.grid, dim3(TC_THREADS), (size_t)tc_smem_for(p.bn), (cudaStream_t)0, op.gemm));
     else gemm_simt_kernel<<<op.grid, 256>>>(op.gemm.p);

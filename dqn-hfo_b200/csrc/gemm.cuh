@@ -35,7 +35,11 @@ struct GemmParams {
   float *out_hi; float *out_lo; int ldo;     // EPI_FWD / EPI_DX
   float *out; long long out_split_stride;     // EPI_PLAIN: out + split*stride
   const float *bias_hi; const float *bias_lo; // EPI_FWD (nullable)
-  const float *mask_hi; const float *mask_lo; int ldmask;  // EPI_DX
+  const float *mask_hi; const float *mask_lo; int ldmask;  // EPI_DX, verification kernel: saved activation
+  // tcgen05 kernel: the ReLU sign of every activation travels as ONE BIT (word (m, n/32), bit n%32 = y > 0).
+  // EPI_FWD writes it next to the activation, EPI_DX reads 4 bytes per 32 columns instead of 256
+  // (the fp32 mask tile was 64 KB of LSU loads per CTA competing with the TMA operand stream).
+  uint32_t *relu_bits_out; const uint32_t *relu_bits_in; int ldbits;
   int apply_lrelu;                            // EPI_FWD: 0 for linear layers
   int bn;                                     // N tile of the tcgen05 kernel: 64 or 128
   int cluster_k;                              // 1: launched as 2-CTA clusters along z; the CTAs split K and the
@@ -278,14 +282,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr));
 }
 
-__device__ __forceinline__ unsigned long long gtime_ns() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-  return t;
-}
-// timeline stamps of CTA (0,0,0) for gemm_test: [0] entry [1] prologue done [2] pdl_wait passed
-// [3] first operands landed [4] accumulators complete [5] epilogue stores issued [6] kernel exit
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// timeline stamps of CTA (0,0,0) for gemm_test / DQNB_TRACE: [0] entry [2] pdl_wait passed [3] first operands
+// landed [4] accumulators complete [5] epilogue stores issued; over all CTAs of the grid: [1] latest pass of
+// pdl_wait, [6] latest exit, [8] latest first-operands, [9] latest accumulators complete, [10] latest epilogue done
 #define DQNB_STAMP(i) do { if (p.dbg_clk && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) p.dbg_clk[i] = (long long)gtime_ns(); } while (0)
+#define DQNB_STAMP_MAX(i) do { if (p.dbg_clk) atomicMax(p.dbg_clk + (i), (long long)gtime_ns()); } while (0)
 
 __device__ __forceinline__ void cluster_arrive_release() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait_acquire() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
@@ -342,12 +345,12 @@ __device__ __forceinline__ void gemm_tc_body(const GemmArgs &args, const int n_t
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  if (threadIdx.x == 0) DQNB_STAMP(1);
   // Everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps the tail of the
   // previous kernel; from here on we read what it wrote.
   pdl_wait();
   pdl_launch_dependents();
   if (threadIdx.x == 0) DQNB_STAMP(2);
+  if (p.dbg_clk && threadIdx.x == 0) atomicMax(p.dbg_clk + 1, (long long)gtime_ns());   // latest CTA to pass the wait
 
   if (warp == 0) {
     // ---------------- TMA producer ----------------
@@ -392,7 +395,7 @@ __device__ __forceinline__ void gemm_tc_body(const GemmArgs &args, const int n_t
       const uint32_t full = bars + 8 * s, empty = bars + 8 * (STAGES + s);
       mbar_wait(full, ph);
       tc_fence_after();
-      if (it == 0 && lane == 0) DQNB_STAMP(3);
+      if (it == 0 && lane == 0) { DQNB_STAMP(3); DQNB_STAMP_MAX(8); }
       const uint32_t sa = base + s * Cfg::STAGE_BYTES, sb = sa + Cfg::A_STAGE_BYTES;
       const uint64_t a_hi = make_desc<A_MN>(sa), a_lo = make_desc<A_MN>(sa + a_lo_off);
       const uint64_t b_hi = make_desc<B_MN>(sb), b_lo = make_desc<B_MN>(sb + b_lo_off);
@@ -469,60 +472,40 @@ __device__ __forceinline__ void gemm_tc_body(const GemmArgs &args, const int n_t
       asm volatile("bar.sync 1, 128;" ::: "memory");
     }
     const int sub = lane / L4 < RPI ? lane / L4 : 0, c4 = (lane % L4) * 4;
-    // EPI_DX: the ReLU' mask source (saved activation tile) does not depend on the MMAs, so its
-    // coalesced loads are issued before waiting for the accumulators and held in registers.
-    constexpr int NPRE = (BN_ == 64) ? 32 / RPI : 1;
-    float4 ypre[NPRE];
-    if (p.epi == EPI_DX && BN_ == 64) {
+    // EPI_DX: the ReLU' sign bits of this thread's row (one word per 32 columns) do not depend on the
+    // MMAs: loaded before waiting for the accumulators.
+    const int m_row = m_tile * BM + q * 32 + lane;
+    uint32_t rbits[BN_ / 32];
 #pragma unroll
-      for (int i = 0; i < NPRE; ++i) {
-        const int r = i * RPI + sub, m = m_tile * BM + q * 32 + r, n = n_base + c4;
-        float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (m < p.M && n < p.N) {
-          const float4 hh = __ldg(reinterpret_cast<const float4 *>(p.mask_hi + (long long)m * p.ldmask + n));
-          const float4 ll = __ldg(reinterpret_cast<const float4 *>(p.mask_lo + (long long)m * p.ldmask + n));
-          y = make_float4(hh.x + ll.x, hh.y + ll.y, hh.z + ll.z, hh.w + ll.w);
-        }
-        ypre[i] = y;
-      }
+    for (int w = 0; w < BN_ / 32; ++w) rbits[w] = 0u;
+    if (p.epi == EPI_DX && m_row < p.M) {
+#pragma unroll
+      for (int w = 0; w < BN_ / 32; ++w)
+        if (n_base + 32 * w < p.N) rbits[w] = __ldg(p.relu_bits_in + (long long)m_row * p.ldbits + (n_base >> 5) + w);
     }
     if (iters > 0) {
       mbar_wait(tfull, 0);
       tc_fence_after();
     }
     if (clus) { cluster_arrive_release(); cluster_wait_acquire(); }   // barrier #1: the peer's partial is visible
-    if (warp == 2 && lane == 0) DQNB_STAMP(4);
-    if (p.epi == EPI_DX) {
-      if (BN_ == 64) {
-#pragma unroll
-        for (int i = 0; i < NPRE; ++i) *reinterpret_cast<float4 *>(st_hi + (i * RPI + sub) * LDS + c4) = ypre[i];
-      } else {
-#pragma unroll 4
-        for (int rr = 0; rr < 32; rr += RPI) {
-          const int r = rr + sub, m = m_tile * BM + q * 32 + r, n = n_base + c4;
-          float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (m < p.M && n < p.N) {
-            const float4 hh = *reinterpret_cast<const float4 *>(p.mask_hi + (long long)m * p.ldmask + n);
-            const float4 ll = *reinterpret_cast<const float4 *>(p.mask_lo + (long long)m * p.ldmask + n);
-            y = make_float4(hh.x + ll.x, hh.y + ll.y, hh.z + ll.z, hh.w + ll.w);
-          }
-          *reinterpret_cast<float4 *>(st_hi + r * LDS + c4) = y;
-        }
-      }
-      __syncwarp();
-    }
+    if (warp == 2 && lane == 0) { DQNB_STAMP(4); DQNB_STAMP_MAX(9); }
     float *my_hi = st_hi + lane * LDS, *my_lo = st_lo + lane * LDS;
-#pragma unroll 1
+    // column chunks of 32: the TMEM loads of chunk c+1 are in flight while chunk c is processed
+    uint32_t ra[2][32], rb[2][32];
+    const uint32_t taddr0 = tmem + ((uint32_t)(q * 32) << 16);
+    if (iters > 0) { tmem_ld32(taddr0, ra[0]); tmem_ld32(taddr0 + BN_, rb[0]); }
+#pragma unroll
     for (int c0 = 0; c0 < BN_; c0 += 32) {
       float v[32];
+      constexpr int kLast = BN_ - 32;
+      const int cur = (c0 >> 5) & 1;
+      const uint32_t bits_in = rbits[c0 / 32];
+      uint32_t bits_out = 0u;
       if (iters > 0) {
-        uint32_t r[32], r2[32];
-        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-        tmem_ld32(taddr, r);
-        tmem_ld32(taddr + BN_, r2);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        tmem_wait_ld();
+        if (c0 < kLast) { tmem_ld32(taddr0 + (uint32_t)(c0 + 32), ra[cur ^ 1]); tmem_ld32(taddr0 + (uint32_t)(c0 + 32) + BN_, rb[cur ^ 1]); }
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + __uint_as_float(r2[j]);
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(ra[cur][j]) + __uint_as_float(rb[cur][j]);
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = 0.f;
@@ -543,9 +526,8 @@ __device__ __forceinline__ void gemm_tc_body(const GemmArgs &args, const int n_t
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
           float o[4], l[4];
-          float4 aux;
+          float4 aux = make_float4(0.f, 0.f, 0.f, 0.f);
           if (p.epi == EPI_FWD) aux = *reinterpret_cast<const float4 *>(s_bias + c0 + j);
-          else aux = *reinterpret_cast<const float4 *>(my_hi + c0 + j);
           const float ax[4] = {aux.x, aux.y, aux.z, aux.w};
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
@@ -553,8 +535,9 @@ __device__ __forceinline__ void gemm_tc_body(const GemmArgs &args, const int n_t
             if (p.epi == EPI_FWD) {
               x += ax[t];                                            // InnerProduct bias
               if (p.apply_lrelu) x = fmaxf(x, 0.f) + kNegSlope * fminf(x, 0.f);
+              bits_out |= (x > 0.f ? 1u : 0u) << (j + t);            // sign of the in-place activation
             } else {
-              x *= (ax[t] > 0.f ? 1.f : kNegSlope);                  // ReLU backward on the in-place activation
+              x *= ((bits_in >> (j + t)) & 1u) ? 1.f : kNegSlope;    // ReLU backward on the in-place activation
             }
             o[t] = tf32_hi(x);
             l[t] = x - o[t];
@@ -562,6 +545,8 @@ __device__ __forceinline__ void gemm_tc_body(const GemmArgs &args, const int n_t
           *reinterpret_cast<float4 *>(my_hi + c0 + j) = make_float4(o[0], o[1], o[2], o[3]);
           *reinterpret_cast<float4 *>(my_lo + c0 + j) = make_float4(l[0], l[1], l[2], l[3]);
         }
+        if (p.epi == EPI_FWD && p.relu_bits_out && m_row < p.M && n_base + c0 < p.N)
+          p.relu_bits_out[(long long)m_row * p.ldbits + ((n_base + c0) >> 5)] = bits_out;
       }
     }
     __syncwarp();
@@ -579,7 +564,7 @@ __device__ __forceinline__ void gemm_tc_body(const GemmArgs &args, const int n_t
         }
       }
     }
-    if (warp == 2 && lane == 0) DQNB_STAMP(5);
+    if (warp == 2 && lane == 0) { DQNB_STAMP(5); DQNB_STAMP_MAX(10); }
     }   // !(cluster peer)
   }
   if (clus) {
@@ -592,6 +577,7 @@ __device__ __forceinline__ void gemm_tc_body(const GemmArgs &args, const int n_t
   }
   tc_fence_before();
   __syncthreads();
+  if (p.dbg_clk && threadIdx.x == 0) atomicMax(p.dbg_clk + 6, (long long)gtime_ns());   // latest CTA exit of the grid
   if (warp == 1) {
     __syncwarp();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(Cfg::TMEM_COLS)

@@ -15,6 +15,26 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 #define DQNB_PDL_PROLOGUE() do { pdl_wait(); pdl_launch_dependents(); } while (0)
 
+// DQNB_TRACE=1 timeline (scripts/trace_update.py): every kernel of the update records, over all its CTAs,
+// [0] the earliest and [1] the latest time a CTA passed griddepcontrol.wait and [2] the latest CTA exit
+// (globaltimer ns; slots preset to ~0 by the host, so min is an unsigned and max a signed atomic).
+constexpr int kTraceSlots = 16;      // int64 slots per op in the trace buffer
+__device__ __forceinline__ unsigned long long gtime_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void trace_begin(long long *t) {
+  if (t && threadIdx.x == 0) {
+    const unsigned long long now = gtime_ns();
+    atomicMin(reinterpret_cast<unsigned long long *>(t), now);
+    atomicMax(t + 1, (long long)now);
+  }
+}
+__device__ __forceinline__ void trace_end(long long *t) {
+  if (t && threadIdx.x == 0) atomicMax(t + 2, (long long)gtime_ns());
+}
+
 constexpr int kGradSplits = 8;      // planes of the gradient-partial buffer
 constexpr int kMaxSegs = 2 * 8 + 4; // parameter blobs per net
 
@@ -79,6 +99,7 @@ __global__ void sample_kernel(const StepState *st, unsigned long long seed, int 
 // -------------------------------------------------------------------------------------------
 // Replay gather (dqn.cpp:859-887): one block per minibatch row, threads along the feature axis.
 struct GatherArgs {
+  long long *trace;              // DQNB_TRACE timeline slot (nullable)
   StepState *st;
   int32_t *idx;                // deque indices of the minibatch rows
   int sample;                  // 1: draw idx on the device (SampleTransitionsFromMemory, dqn.cpp:501-509)
@@ -94,6 +115,7 @@ struct GatherArgs {
 
 __global__ void __launch_bounds__(128) gather_kernel(const GatherArgs a) {
   DQNB_PDL_PROLOGUE();
+  trace_begin(a.trace);
   const int n = blockIdx.x;
   const bool valid = n < a.B;
   if (n == 0 && threadIdx.x == 32) {
@@ -154,6 +176,7 @@ __global__ void __launch_bounds__(128) gather_kernel(const GatherArgs a) {
     a.mc[n] = valid ? a.ring_misc[phys * a.rw + 11] : 0.f;
     a.term[n] = misc_term;
   }
+  trace_end(a.trace);
 }
 
 // -------------------------------------------------------------------------------------------
@@ -170,6 +193,7 @@ __device__ __forceinline__ double warp_sum_d(double v) {
 
 // Linear heads (dqn.cpp:426-427, :450): out[n][j] = h[n] . W[j] + b[j], one warp per row.
 struct HeadArgs {
+  long long *trace;              // DQNB_TRACE timeline slot (nullable)
   const float *H; long long h_plane; int ldh; int Kp;   // top tower activation [2][rows][ldh]
   const float *W; long long w_plane;                    // head weights [2][..] rows of Kp
   const float *bias; long long b_plane;
@@ -203,6 +227,7 @@ __device__ __forceinline__ float4 relu_bwd4(const float4 v, const float4 y) {
 
 __global__ void __launch_bounds__(256) head_fwd_kernel(const HeadArgs a) {
   DQNB_PDL_PROLOGUE();
+  trace_begin(a.trace);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = blockIdx.x * kHeadRowsPerBlock + warp;
   if (n >= a.rows) return;
@@ -236,6 +261,7 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const HeadArgs a) {
       a.dst[o] = h; a.dst[o + a.dst_plane] = v - h;
     }
   }
+  trace_end(a.trace);
 }
 
 // Critic head, fused per minibatch row (one warp per row):
@@ -247,6 +273,7 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const HeadArgs a) {
 //   dZ[n][k] = dq * w_q[k] * relu'(h[n][k])
 enum { QMODE_TARGET = 0, QMODE_LOSS = 1, QMODE_POLICY = 2 };
 struct CriticHeadArgs {
+  long long *trace;              // DQNB_TRACE timeline slot (nullable)
   int mode, B, rows_pad;
   const float *H; long long h_plane; int ldh; int Kp;
   const float *W; long long w_plane; const float *bias; long long b_plane;
@@ -260,6 +287,7 @@ struct CriticHeadArgs {
 };
 __global__ void __launch_bounds__(256) critic_head_kernel(const CriticHeadArgs a) {
   DQNB_PDL_PROLOGUE();
+  trace_begin(a.trace);
   __shared__ double red[8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = blockIdx.x * kHeadRowsPerBlock + warp;
@@ -298,20 +326,21 @@ __global__ void __launch_bounds__(256) critic_head_kernel(const CriticHeadArgs a
       }
     }
   }
-  if (a.mode == QMODE_TARGET) return;
   if (lane == 0) red[warp] = contrib;
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0 && a.mode != QMODE_TARGET) {
     double s = 0.0;
     for (int w = 0; w < 8; ++w) s += red[w];
     a.part[blockIdx.x] = s;
   }
+  trace_end(a.trace);
 }
 
 // Actor heads backward, fused per row: inverting gradients (dqn.cpp:927-957) on the critic's input
 // diff columns [S, S+10), then Split-sum of the two heads' bottom diffs and the ReLU' of the tower top:
 //   dZ[n][k] = (sum_j d10[n][j] * W[j][k]) * relu'(h[n][k])
 struct ActorHeadBwdArgs {
+  long long *trace;              // DQNB_TRACE timeline slot (nullable)
   int B, rows_pad, S, ldin;
   const float *d_in;           // [din_splits][Bp][ldin] fp32 split-K partials of dL/d(critic input)
   int din_splits; long long din_stride;
@@ -324,6 +353,7 @@ struct ActorHeadBwdArgs {
 };
 __global__ void __launch_bounds__(256) actor_head_bwd_kernel(const ActorHeadBwdArgs a) {
   DQNB_PDL_PROLOGUE();
+  trace_begin(a.trace);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = blockIdx.x * kHeadRowsPerBlock + warp;
   if (n >= a.rows_pad) return;
@@ -360,6 +390,7 @@ __global__ void __launch_bounds__(256) actor_head_bwd_kernel(const ActorHeadBwdA
     }
     store_split4(zh + k, zl + k, relu_bwd4(acc, y));
   }
+  if (warp == 0) trace_end(a.trace);
 }
 
 // Head weight/bias gradients: dW[j][k] = sum_n d16[n][j] h[n][k] ; db[j] = sum_n d16[n][j].
@@ -368,6 +399,7 @@ __global__ void __launch_bounds__(256) actor_head_bwd_kernel(const ActorHeadBwdA
 constexpr int kRedSub = 8;
 constexpr int kHbwCols = 32;
 struct HeadBwdWArgs {
+  long long *trace;              // DQNB_TRACE timeline slot (nullable)
   const float *d16; int J;
   const float *H; long long h_plane; int ldh; int Kp;
   int rows_pad;
@@ -375,6 +407,7 @@ struct HeadBwdWArgs {
 };
 __global__ void __launch_bounds__(256) head_bwd_w_kernel(const HeadBwdWArgs a) {
   DQNB_PDL_PROLOGUE();
+  trace_begin(a.trace);
   __shared__ float red[kRedSub][kActorOut][kHbwCols];
   __shared__ float sd[128 * 16];             // up to 128 rows of d16 per chunk
   const int col = threadIdx.x & (kHbwCols - 1), sub = threadIdx.x / kHbwCols, split = blockIdx.y;
@@ -416,10 +449,12 @@ __global__ void __launch_bounds__(256) head_bwd_w_kernel(const HeadBwdWArgs a) {
     }
   }
   if (blockIdx.x == 0 && sub == 0 && col < a.J) g[a.hb_off + col] = bias_acc;
+  trace_end(a.trace);
 }
 
 // Bias gradients of the tower layers: db_l[c] = sum_n dZ_l[n][c] (Caffe: gemv(dY^T, ones)).
 struct ColsumArgs {
+  long long *trace;              // DQNB_TRACE timeline slot (nullable)
   int n_layers, rows_pad;
   const float *dZ[8]; long long plane[8]; int ld[8]; int Np[8]; long long b_off[8];
   int blk_begin[9];            // prefix sums of Np/128 column blocks
@@ -427,6 +462,7 @@ struct ColsumArgs {
 };
 __global__ void __launch_bounds__(1024) colsum_kernel(const ColsumArgs a) {
   DQNB_PDL_PROLOGUE();
+  trace_begin(a.trace);
   __shared__ float red[kRedSub][128];
   int l = 0;
   while (l + 1 < a.n_layers && (int)blockIdx.x >= a.blk_begin[l + 1]) ++l;
@@ -452,6 +488,7 @@ __global__ void __launch_bounds__(1024) colsum_kernel(const ColsumArgs a) {
     for (int t = 0; t < kRedSub; ++t) s += red[t][col];
     a.gpart[(long long)split * a.gpart_stride + a.b_off[l] + c] = s;
   }
+  trace_end(a.trace);
 }
 
 // -------------------------------------------------------------------------------------------
@@ -462,6 +499,7 @@ struct SegTable {
   int nsplit[kMaxSegs];
 };
 struct ReduceArgs {
+  long long *trace;              // DQNB_TRACE timeline slot (nullable)
   SegTable segs;
   long long flat;
   const float *gpart; long long gpart_stride;
@@ -472,6 +510,7 @@ struct ReduceArgs {
 };
 __global__ void __launch_bounds__(256) reduce_kernel(const ReduceArgs a) {
   DQNB_PDL_PROLOGUE();
+  trace_begin(a.trace);
   const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   float ss = 0.f;
   if (i < a.flat) {
@@ -507,10 +546,12 @@ __global__ void __launch_bounds__(256) reduce_kernel(const ReduceArgs a) {
     for (int j = 0; j < a.n_scal; ++j) s += a.scal_part[j];
     a.G[a.flat] = (float)(s * (double)a.scal_scale);
   }
+  trace_end(a.trace);
 }
 
 // ClipGradients scale + AdamSolver::ComputeUpdateValue + Net::Update (+ SoftUpdateNet dqn.cpp:1085-1096)
 struct AdamArgs {
+  long long *trace;              // DQNB_TRACE timeline slot (nullable)
   long long flat;
   const float *G;
   const float *norm_part; int n_norm;
@@ -541,6 +582,7 @@ __device__ __forceinline__ void adam_finalize(const AdamArgs &a) {
 }
 __global__ void __launch_bounds__(256) adam_kernel(const AdamArgs a) {
   DQNB_PDL_PROLOGUE();
+  trace_begin(a.trace);
   __shared__ float s_scale;
   __shared__ double red[8];
   {
@@ -561,6 +603,7 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamArgs a) {
   const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i >= a.flat) {
     if (a.finalize) adam_finalize(a);
+    trace_end(a.trace);
     return;
   }
   const float scale = s_scale;
@@ -607,6 +650,7 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamArgs a) {
     *reinterpret_cast<float4 *>(a.T + a.t_plane + i) = make_float4(ol[0], ol[1], ol[2], ol[3]);
   }
   if (a.finalize) adam_finalize(a);
+  trace_end(a.trace);
 }
 
 // -------------------------------------------------------------------------------------------
@@ -625,6 +669,7 @@ struct P2PTable {                 // device-resident, filled by dqnb_comm_p2p_in
   float *base[kMaxPeers];         // peer exchange allocations (IPC-mapped); base[rank] is our own
 };
 struct P2PArgs {
+  long long *trace;              // DQNB_TRACE timeline slot (nullable)
   const P2PTable *tab;
   int world, rank, net;
   long long in_off, out_off;      // float offsets of this net's input / output buffer inside an exchange allocation
@@ -661,6 +706,7 @@ __device__ __forceinline__ bool spin_until_ge(const unsigned int *flag, unsigned
 }
 __global__ void __launch_bounds__(512) p2p_allreduce_kernel(const P2PArgs a) {
   DQNB_PDL_PROLOGUE();
+  trace_begin(a.trace);
   __shared__ int s_last;
   const int W = a.world;
   const unsigned int e = a.epoch[a.net] + 1u;

@@ -13,8 +13,8 @@ def run(M,N,K,sp,bn,a_mn=0,b_mn=0):
     Ain = np.ascontiguousarray(A.T) if a_mn else A
     Bin = np.ascontiguousarray(B.T) if b_mn else B
     _, ms = P.gemm_test(0 | ((bn<<8)<<8), a_mn, b_mn, M, N, K, sp, Ain, Bin)
-    c = (C.c_longlong*(8*21))(); L.dqnb_gemm_test_clocks(c, 8*21)
-    t = np.array(list(c), dtype=np.int64).reshape(21, 8)[:, :7]
+    c = (C.c_longlong*(16*21))(); L.dqnb_gemm_test_clocks(c, 16*21)
+    t = np.array(list(c), dtype=np.int64).reshape(21, 16)[:, :7]
     return ms*1e3, t
 for (M,N,K,sp,bn,tag,a,b) in [(1024,1024,64,1,64,"L1fwd",0,0),(1024,128,256,1,64,"L4fwd",0,0),(1024,512,1024,1,64,"L2fwd",0,0),(1024,512,1024,4,128,"L2fwd sp4 bn128",0,0),
                               (1024,256,512,1,64,"L3fwd",0,0),(128,256,1024,8,64,"L4dW",1,1)]:

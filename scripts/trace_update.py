@@ -1,4 +1,10 @@
-"""GPU: timeline of the GEMM launches of one update (DQNB_TRACE=1), from in-kernel globaltimer stamps."""
+"""GPU: timeline of every kernel of one update (DQNB_TRACE=1), from in-kernel globaltimer stamps.
+
+usage: python scripts/trace_update.py [batch]
+GEMM rows : CTA (0,0,0): entry, pdl_wait passed, first operands, accumulators done, epilogue stores issued;
+            grid-wide: latest CTA to pass pdl_wait, latest CTA exit.
+other rows: earliest / latest CTA past pdl_wait, latest exit of thread 0 of any CTA.
+"""
 import os, sys, ctypes as C
 os.environ["DQNB_TRACE"] = "1"
 import numpy as np
@@ -10,27 +16,43 @@ L = P.lib()
 L.dqnb_debug_trace.argtypes = [C.c_void_p, C.POINTER(C.c_longlong), C.c_int64]
 L.dqnb_debug_trace.restype = C.c_int64
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+if len(sys.argv) > 2:          # knob overrides, e.g. '{"DQNB_SCHED": 1}'
+    import json
+    for k, v in json.loads(sys.argv[2]).items():
+        os.environ[k] = str(v)
+    print("knobs:", sys.argv[2])
 d = P.DQNB(state_size=58, batch=B, hidden=(1024, 512, 256, 128), replay_capacity=70000, use_graph=1)
 d.init_params(2, 0.01)
 s, a, r, mc, term, sn = synth_replay(65536, 58, 1)
 d.add_transitions(s, a, r, mc, sn, term)
 d.update(20)
 ms = d.benchmark(200)
-print(f"graph replay: {ms/200*1e3:.1f} us per update")
+print(f"graph replay (tracing on): {ms/200*1e3:.1f} us per update")
 d.update(1)
-buf = (C.c_longlong * 4096)()
-n = L.dqnb_debug_trace(d._h, buf, 4096)
-t = np.array(list(buf[:n]), dtype=np.int64).reshape(-1, 8)
-kinds = ["GEMM","GATHER","SAMPLE","HEAD_FWD","CRITIC_HEAD","ACTOR_HEAD_BWD","HEAD_BWD_W","COLSUM","REDUCE","ALLREDUCE","P2P_ALLREDUCE","ADAM","PREP","FINALIZE","FORK","JOIN"]
-g = [i for i in range(len(t)) if t[i,7]//1000 == 0]
-t0 = min(t[i,0] for i in g)
-print(" op kind        br grid(x,y,z) kb |  entry  pdlwait  operands acc_done epi_done | dur(after wait)")
+buf = (C.c_longlong * 16384)()
+n = L.dqnb_debug_trace(d._h, buf, 16384)
+t = np.array(list(buf[:n]), dtype=np.int64).reshape(-1, 16)
+kinds = ["GEMM", "GEMM_GROUP", "GATHER", "SAMPLE", "HEAD_FWD", "CRITIC_HEAD", "ACTOR_HEAD_BWD", "HEAD_BWD_W", "COLSUM",
+         "REDUCE", "ALLREDUCE", "P2P_ALLREDUCE", "ADAM", "PREP", "FINALIZE", "FORK", "JOIN"]
+valid = t[:, 0] > 0
+t0 = t[valid, 0].min()
+us = lambda v: (v - t0) / 1e3 if v > 0 else float("nan")
+print(" op kind           br grid(x,y,z)  kb |  entry  waited(all)  operands(all)  acc_done(all)  epi_done(all) exit(all) | wait->exit")
 for i in range(len(t)):
-    k, br = int(t[i,7]//1000), int(t[i,7]%1000)
-    if k != 0:
-        print(f"{i:3d} {kinds[k]:14s} {br}")
+    meta = int(t[i, 7])
+    k, br = (meta & 0xffff) // 1000, (meta & 0xffff) % 1000
+    name = kinds[k] if k < len(kinds) else str(k)
+    if name in ("FORK", "JOIN"):
+        print(f"{i:3d} {name:16s}")
         continue
-    gx, gy, gz, kb = (t[i,6]>>40)&0xfff, (t[i,6]>>20)&0xfffff, t[i,6]&0xfffff, (t[i,6]>>52)
-    e = [(t[i,j]-t0)/1e3 for j in range(6)]
-    print(f"{i:3d} GEMM           {br} ({gx:2d},{gy:2d},{gz:2d}) {kb:3d} | {e[0]:7.1f} {e[2]:7.1f} {e[3]:8.1f} {e[4]:8.1f} {e[5]:8.1f} | {e[5]-e[2]:6.1f}")
+    if t[i, 0] <= 0:
+        print(f"{i:3d} {name:16s} {br}   (not launched)")
+        continue
+    if name == "GEMM":
+        gx, gy, gz, kb = (meta >> 16) & 0xfff, (meta >> 28) & 0xfff, (meta >> 40) & 0xff, (meta >> 48) & 0xfff
+        print(f"{i:3d} {name:16s} {br} ({gx:2d},{gy:2d},{gz:2d}) {kb:3d} | {us(t[i,0]):7.1f} {us(t[i,2]):6.1f}({us(t[i,1]):6.1f}) "
+              f"{us(t[i,3]):6.1f}({us(t[i,8]):6.1f}) {us(t[i,4]):6.1f}({us(t[i,9]):6.1f}) {us(t[i,5]):6.1f}({us(t[i,10]):6.1f}) {us(t[i,6]):8.1f} | {us(t[i,6]) - us(t[i,2]):6.1f}")
+    else:
+        print(f"{i:3d} {name:16s} {br}                  | {'':7s} {us(t[i,0]):6.1f}({us(t[i,1]):6.1f}) {'':14s} {'':14s} {'':14s} {us(t[i,2]):8.1f} | "
+              f"{us(t[i,2]) - us(t[i,0]):6.1f}")
 d.close()
