@@ -63,6 +63,24 @@ static int make_tmap(CUtensorMap *tm, const float *base, int rows, int ld, long 
   return 0;
 }
 
+// Output of a GEMM as the TMA unit stores it: fp32 [d2][rows][ld] clipped to `cols` columns, box {32, 32, box_d2},
+// 128-byte swizzle (the epilogue stages its boxes in that pattern, gemm.cuh).
+static int make_tmap_out(CUtensorMap *tm, const float *base, int cols, int rows, int d2, int ld, long long d2_stride_elems,
+                         int box_d2) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) DQNB_FAIL("cuTensorMapEncodeTiled entry point not available");
+  if (d2_stride_elems <= 0) d2_stride_elems = (long long)rows * ld;
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)d2};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 4ull, (cuuint64_t)d2_stride_elems * 4ull};
+  cuuint32_t box[3] = {32, 32, (cuuint32_t)box_d2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)base, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) DQNB_FAIL("cuTensorMapEncodeTiled (output) failed with CUresult %d (rows=%d ld=%d d2=%d)", (int)r, rows, ld, d2);
+  return 0;
+}
+
 // ---------------------------------------------------------------------------------------------
 // NCCL through dlopen (only when world_size > 1)
 // ---------------------------------------------------------------------------------------------
@@ -373,6 +391,11 @@ static int finish_gemm(const dqnb_config &cfg, Op *op) {
     }
     if (make_tmap(&op->gemm.tmA, p.A, a_rows, p.lda, p.a_plane, p.a_mn ? 32 : BM, p.a_mn != 0)) return -1;
     if (make_tmap(&op->gemm.tmB, p.B, b_rows, p.ldb, p.b_plane, p.b_mn ? 32 : p.bn, p.b_mn != 0)) return -1;
+    if (p.epi == EPI_PLAIN) {
+      if (make_tmap_out(&op->gemm.tmD, p.out, p.N, p.M, p.splits, p.ldo, p.out_split_stride, 1)) return -1;
+    } else {
+      if (make_tmap_out(&op->gemm.tmD, p.out_hi, p.N, p.M, 2, p.ldo, (long long)(p.out_lo - p.out_hi), 2)) return -1;
+    }
     op->grid = dim3((p.N + p.bn - 1) / p.bn, (p.M + BM - 1) / BM, p.splits);
   } else {
     op->grid = dim3((p.N + ST - 1) / ST, (p.M + ST - 1) / ST, p.splits);

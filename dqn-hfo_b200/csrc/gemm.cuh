@@ -51,6 +51,7 @@ struct GemmParams {
 struct alignas(64) GemmArgs {
   CUtensorMap tmA;
   CUtensorMap tmB;
+  CUtensorMap tmD;      // output: {ldo, M, 2 planes} (EPI_FWD / EPI_DX) or {ldo, M, splits} (EPI_PLAIN), box {32, 32, 2 | 1}
   GemmParams p;
 };
 
@@ -222,6 +223,18 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *tm,
       "[%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
       : "memory");
 }
+// TMA store of one staged box (128B-swizzled in shared memory) + bulk-group bookkeeping of the issuing thread
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap *tm, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(tm), "r"(src),
+               "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void st_smem_f4(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 }
@@ -331,6 +344,7 @@ __device__ __forceinline__ void gemm_tc_body(const GemmArgs &args, const int n_t
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&args.tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&args.tmB) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&args.tmD) : "memory");
     for (int i = 0; i < 2 * STAGES + 1; ++i) mbar_init(bars + 8 * i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -423,22 +437,22 @@ __device__ __forceinline__ void gemm_tc_body(const GemmArgs &args, const int n_t
     }
     __syncwarp();
   } else {
-    // ---------------- epilogue: TMEM -> registers -> smem -> coalesced HBM ----------------
-    // TMEM hands every thread one accumulator ROW, but a row-per-thread global store touches 32
-    // different 256-byte segments per instruction (measured 4.2 us per tile).  All TMA loads have
-    // been consumed once tfull fires, so the pipeline stages are reused as a staging tile: each warp
-    // transposes its own 32 rows through shared memory (row stride BN+4 floats keeps the float4
-    // accesses conflict-free) and then writes whole rows with consecutive lanes.
-    constexpr int LDS = BN_ + 4;
-    constexpr int L4 = BN_ / 4;              // float4 per row
-    constexpr int RPI = 32 / L4 > 0 ? 32 / L4 : 1;   // rows per warp-wide store instruction (BN=64: 2)
+    // ---------------- epilogue: TMEM -> registers -> swizzled smem -> TMA store ----------------
+    // TMEM hands every thread one accumulator ROW.  All TMA loads have been consumed once tfull fires, so
+    // the pipeline stages are reused as staging: per 32-column chunk every warp writes its 32 rows x 128 B
+    // (x 2 planes) in the 128B-swizzle pattern (16-byte slot j of row r at slot j ^ (r & 7): conflict-free
+    // float4 stores) and one lane hands the box to the TMA unit, which writes full lines to L2 and clips
+    // the rows / columns outside the matrix.  (Row-per-thread global stores: 4.2 us per tile; staged and
+    // re-read by the threads for coalesced stores: 2.5 us.)
+    constexpr int LDS = BN_ + 4;             // row stride of the split-K peer's raw partial tile
+    constexpr int NCH = BN_ / 32;            // 32-column chunks
     static_assert(BN_ == 64 || BN_ == 128, "epilogue mapping assumes BN of 64 or 128");
-    static_assert(2 * BM * LDS * 4 <= STAGES * Cfg::STAGE_BYTES, "staging tile must fit in the stage ring");
+    static_assert(BM * LDS * 4 <= STAGES * Cfg::STAGE_BYTES, "peer partial tile must fit in the stage ring");
+    static_assert(4 * NCH * 2 * 4096 <= STAGES * Cfg::STAGE_BYTES, "staging boxes must fit in the stage ring");
     const int q = warp & 3;                  // TMEM lane quarter this warp may read
     const int et = threadIdx.x - 64;         // 0..127 inside the epilogue warps
     float *s_bias = reinterpret_cast<float *>(base_ptr + STAGES * Cfg::STAGE_BYTES + 256);
     float *st_hi = reinterpret_cast<float *>(base_ptr) + (q * 32) * LDS;
-    float *st_lo = st_hi + BM * LDS;
     const int n_base = n_tile * BN_;
     if (clus && crank == 1) {
       // split-K peer: publish the raw partial tile in this CTA's staging area; the leader reads it over
@@ -471,7 +485,6 @@ __device__ __forceinline__ void gemm_tc_body(const GemmArgs &args, const int n_t
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
     }
-    const int sub = lane / L4 < RPI ? lane / L4 : 0, c4 = (lane % L4) * 4;
     // EPI_DX: the ReLU' sign bits of this thread's row (one word per 32 columns) do not depend on the
     // MMAs: loaded before waiting for the accumulators.
     const int m_row = m_tile * BM + q * 32 + lane;
@@ -489,7 +502,10 @@ __device__ __forceinline__ void gemm_tc_body(const GemmArgs &args, const int n_t
     }
     if (clus) { cluster_arrive_release(); cluster_wait_acquire(); }   // barrier #1: the peer's partial is visible
     if (warp == 2 && lane == 0) { DQNB_STAMP(4); DQNB_STAMP_MAX(9); }
-    float *my_hi = st_hi + lane * LDS, *my_lo = st_lo + lane * LDS;
+    const float *peer_row = st_hi + lane * LDS;          // same offset inside the peer CTA's shared memory
+    const uint32_t box0 = base + (uint32_t)(q * NCH) * 8192u;   // this warp's staging boxes: [chunk][plane][32 rows][128 B]
+    const uint32_t row_off = (uint32_t)lane * 128u, sw = (uint32_t)(lane & 7);
+    const int planes_out = p.epi == EPI_PLAIN ? 1 : 2;
     // column chunks of 32: the TMEM loads of chunk c+1 are in flight while chunk c is processed
     uint32_t ra[2][32], rb[2][32];
     const uint32_t taddr0 = tmem + ((uint32_t)(q * 32) << 16);
@@ -511,17 +527,18 @@ __device__ __forceinline__ void gemm_tc_body(const GemmArgs &args, const int n_t
         for (int j = 0; j < 32; ++j) v[j] = 0.f;
       }
       if (clus) {                            // + the other half of K, from the peer CTA's shared memory
-        const uint32_t mine = smem_u32(my_hi + c0);
+        const uint32_t mine = smem_u32(peer_row + c0);
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
           const float4 pp = ld_dsmem_f4(mine + j * 4, 1u);
           v[j] += pp.x; v[j + 1] += pp.y; v[j + 2] += pp.z; v[j + 3] += pp.w;
         }
       }
+      const uint32_t box = box0 + (uint32_t)(c0 >> 5) * 8192u + row_off;
       if (p.epi == EPI_PLAIN) {
 #pragma unroll
         for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<float4 *>(my_hi + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          st_smem_f4(box + ((((uint32_t)j >> 2) ^ sw) << 4), v[j], v[j + 1], v[j + 2], v[j + 3]);
       } else {
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
@@ -542,28 +559,23 @@ __device__ __forceinline__ void gemm_tc_body(const GemmArgs &args, const int n_t
             o[t] = tf32_hi(x);
             l[t] = x - o[t];
           }
-          *reinterpret_cast<float4 *>(my_hi + c0 + j) = make_float4(o[0], o[1], o[2], o[3]);
-          *reinterpret_cast<float4 *>(my_lo + c0 + j) = make_float4(l[0], l[1], l[2], l[3]);
+          const uint32_t slot = box + ((((uint32_t)j >> 2) ^ sw) << 4);
+          st_smem_f4(slot, o[0], o[1], o[2], o[3]);
+          st_smem_f4(slot + 4096u, l[0], l[1], l[2], l[3]);
         }
         if (p.epi == EPI_FWD && p.relu_bits_out && m_row < p.M && n_base + c0 < p.N)
           p.relu_bits_out[(long long)m_row * p.ldbits + ((n_base + c0) >> 5)] = bits_out;
       }
-    }
-    __syncwarp();
-    {
-      float *g_hi, *g_lo = nullptr;
-      if (p.epi == EPI_PLAIN) g_hi = p.out + (long long)split * p.out_split_stride;
-      else { g_hi = p.out_hi; g_lo = p.out_lo; }
-#pragma unroll 4
-      for (int rr = 0; rr < 32; rr += RPI) {
-        const int r = rr + sub, m = m_tile * BM + q * 32 + r, n = n_base + c4;
-        if (m < p.M && n < p.N) {
-          const long long o = (long long)m * p.ldo + n;
-          *reinterpret_cast<float4 *>(g_hi + o) = *reinterpret_cast<const float4 *>(st_hi + r * LDS + c4);
-          if (g_lo) *reinterpret_cast<float4 *>(g_lo + o) = *reinterpret_cast<const float4 *>(st_lo + r * LDS + c4);
-        }
+      // hand this chunk's box (both planes) to the TMA unit; the next chunk is staged meanwhile
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0 && n_base + c0 < p.N && m_tile * BM + q * 32 < p.M) {
+        tma_store_3d(&args.tmD, box - row_off, n_base + c0, m_tile * BM + q * 32, planes_out == 1 ? split : 0);
+        bulk_commit();
       }
     }
+    if (lane == 0) bulk_wait_all();          // the boxes have been read and written before shared memory goes away
+    __syncwarp();
     if (warp == 2 && lane == 0) { DQNB_STAMP(5); DQNB_STAMP_MAX(10); }
     }   // !(cluster peer)
   }
