@@ -13,7 +13,7 @@
 // gemm_tc_kernel   : TMA (cp.async.bulk.tensor.3d, 128B swizzle) -> 4-stage smem ring ->
 //                    tcgen05.mma.cta_group::1.kind::tf32 (M128 x N64 x K8, fp32 accumulators in
 //                    TMEM) -> tcgen05.ld epilogue.  Warp roles: 0 = TMA producer, 1 = MMA issuer
-//                    (+ TMEM alloc), 2..5 = epilogue (one TMEM lane quarter each).
+//                    (+ TMEM alloc); all 8 warps run the epilogue (two per TMEM lane quarter).
 // gemm_simt_kernel : plain FFMA tiles over the same operands/epilogues (verification mode).
 #pragma once
 #include "common.cuh"
@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmParams p) {
 // tcgen05 / TMA / TMEM kernel
 // ---------------------------------------------------------------------------------------------
 constexpr int BM = 128, BK = 32;
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 256;   // warp 0: TMA producer, warp 1: MMA issuer (+ TMEM alloc); all 8 run the epilogue
 constexpr int TC_SMEM_MAX = 232448;                   // 227 KB: the per-CTA maximum on sm_100
 
 template <int BN_>
@@ -436,37 +436,64 @@ __device__ __forceinline__ void gemm_tc_body(const GemmArgs &args, const int n_t
       tc_commit(tfull);                    // accumulators complete -> epilogue
     }
     __syncwarp();
-  } else {
+  }
+  {
     // ---------------- epilogue: TMEM -> registers -> swizzled smem -> TMA store ----------------
+    // All eight warps take part (the producer and the MMA issuer join when their loops are done): warp w may
+    // read TMEM lane quarter w % 4, so warps w and w + 4 share a quarter and split its 32-column chunks.
     // TMEM hands every thread one accumulator ROW.  All TMA loads have been consumed once tfull fires, so
-    // the pipeline stages are reused as staging: per 32-column chunk every warp writes its 32 rows x 128 B
-    // (x 2 planes) in the 128B-swizzle pattern (16-byte slot j of row r at slot j ^ (r & 7): conflict-free
-    // float4 stores) and one lane hands the box to the TMA unit, which writes full lines to L2 and clips
-    // the rows / columns outside the matrix.  (Row-per-thread global stores: 4.2 us per tile; staged and
-    // re-read by the threads for coalesced stores: 2.5 us.)
+    // the pipeline stages are reused as staging: per chunk a warp writes its 32 rows x 128 B (x 2 planes) in
+    // the 128B-swizzle pattern (16-byte slot j of row r at slot j ^ (r & 7): conflict-free float4 stores)
+    // and one lane hands the box to the TMA unit, which writes full lines to L2 and clips the rows / columns
+    // outside the matrix.  (Row-per-thread global stores: 4.2 us per tile; staged and re-read by the threads
+    // for coalesced stores: 2.5 us.)
     constexpr int LDS = BN_ + 4;             // row stride of the split-K peer's raw partial tile
-    constexpr int NCH = BN_ / 32;            // 32-column chunks
+    constexpr int NCH = BN_ / 32;            // 32-column chunks of the tile
+    constexpr int MYCH = NCH / 2;            // ... handled by this warp: chunks half, half + 2, ..
     static_assert(BN_ == 64 || BN_ == 128, "epilogue mapping assumes BN of 64 or 128");
     static_assert(BM * LDS * 4 <= STAGES * Cfg::STAGE_BYTES, "peer partial tile must fit in the stage ring");
     static_assert(4 * NCH * 2 * 4096 <= STAGES * Cfg::STAGE_BYTES, "staging boxes must fit in the stage ring");
     const int q = warp & 3;                  // TMEM lane quarter this warp may read
-    const int et = threadIdx.x - 64;         // 0..127 inside the epilogue warps
+    const int half = warp >> 2;
     float *s_bias = reinterpret_cast<float *>(base_ptr + STAGES * Cfg::STAGE_BYTES + 256);
     float *st_hi = reinterpret_cast<float *>(base_ptr) + (q * 32) * LDS;
     const int n_base = n_tile * BN_;
-    if (clus && crank == 1) {
+    const bool peer = clus && crank == 1;
+    if (warp >= 2 && !peer && p.epi == EPI_FWD) {    // stage the tile's bias once (overlaps the mainloop)
+      for (int t = threadIdx.x - 64; t < BN_; t += TC_THREADS - 64) {
+        const int n = n_base + t;
+        s_bias[t] = (p.bias_hi && n < p.N) ? p.bias_hi[n] + p.bias_lo[n] : 0.f;
+      }
+    }
+    // EPI_DX: the ReLU' sign bits of this thread's row (one word per 32 columns) do not depend on the
+    // MMAs: loaded before waiting for the accumulators.
+    const int m_row = m_tile * BM + q * 32 + lane;
+    uint32_t rbits[MYCH];
+#pragma unroll
+    for (int i = 0; i < MYCH; ++i) {
+      const int c0 = (half + 2 * i) * 32;
+      rbits[i] = 0u;
+      if (!peer && p.epi == EPI_DX && m_row < p.M && n_base + c0 < p.N)
+        rbits[i] = __ldg(p.relu_bits_in + (long long)m_row * p.ldbits + ((n_base + c0) >> 5));
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(TC_THREADS) : "memory");   // bias tile visible; warps 0/1 are done issuing
+    if (iters > 0) {
+      mbar_wait(tfull, 0);
+      tc_fence_after();
+    }
+    const uint32_t taddr0 = tmem + ((uint32_t)(q * 32) << 16);
+    if (peer) {
       // split-K peer: publish the raw partial tile in this CTA's staging area; the leader reads it over
       // distributed shared memory after cluster barrier #1 (below) and runs the real epilogue
-      if (iters > 0) { mbar_wait(tfull, 0); tc_fence_after(); }
       float *mine = st_hi + lane * LDS;
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN_; c0 += 32) {
+#pragma unroll
+      for (int i = 0; i < MYCH; ++i) {
+        const int c0 = (half + 2 * i) * 32;
         uint32_t r[32], r2[32];
         if (iters > 0) {
-          const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-          tmem_ld32(taddr, r);
-          tmem_ld32(taddr + BN_, r2);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          tmem_ld32(taddr0 + (uint32_t)c0, r);
+          tmem_ld32(taddr0 + (uint32_t)c0 + BN_, r2);
+          tmem_wait_ld();
         } else {
 #pragma unroll
           for (int j = 0; j < 32; ++j) { r[j] = 0u; r2[j] = 0u; }
@@ -478,112 +505,92 @@ __device__ __forceinline__ void gemm_tc_body(const GemmArgs &args, const int n_t
                           __uint_as_float(r[j + 2]) + __uint_as_float(r2[j + 2]), __uint_as_float(r[j + 3]) + __uint_as_float(r2[j + 3]));
       }
     } else {
-    if (p.epi == EPI_FWD) {                  // stage the tile's bias once (overlaps the mainloop)
-      for (int t = et; t < BN_; t += 128) {
-        const int n = n_base + t;
-        s_bias[t] = (p.bias_hi && n < p.N) ? p.bias_hi[n] + p.bias_lo[n] : 0.f;
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-    }
-    // EPI_DX: the ReLU' sign bits of this thread's row (one word per 32 columns) do not depend on the
-    // MMAs: loaded before waiting for the accumulators.
-    const int m_row = m_tile * BM + q * 32 + lane;
-    uint32_t rbits[BN_ / 32];
+      // the TMEM loads of this warp's first chunk go out before the (cluster) hand-shake
+      uint32_t ra[2][32], rb[2][32];
+      if (iters > 0) { tmem_ld32(taddr0 + (uint32_t)(half * 32), ra[0]); tmem_ld32(taddr0 + (uint32_t)(half * 32) + BN_, rb[0]); }
+      if (clus) { cluster_arrive_release(); cluster_wait_acquire(); }   // barrier #1: the peer's partial is visible
+      if (warp == 2 && lane == 0) { DQNB_STAMP(4); DQNB_STAMP_MAX(9); }
+      const float *peer_row = st_hi + lane * LDS;          // same offset inside the peer CTA's shared memory
+      const uint32_t box0 = base + (uint32_t)(q * NCH) * 8192u;   // staging boxes: [quarter][chunk][plane][32 rows][128 B]
+      const uint32_t row_off = (uint32_t)lane * 128u, sw = (uint32_t)(lane & 7);
+      const int planes_out = p.epi == EPI_PLAIN ? 1 : 2;
 #pragma unroll
-    for (int w = 0; w < BN_ / 32; ++w) rbits[w] = 0u;
-    if (p.epi == EPI_DX && m_row < p.M) {
-#pragma unroll
-      for (int w = 0; w < BN_ / 32; ++w)
-        if (n_base + 32 * w < p.N) rbits[w] = __ldg(p.relu_bits_in + (long long)m_row * p.ldbits + (n_base >> 5) + w);
-    }
-    if (iters > 0) {
-      mbar_wait(tfull, 0);
-      tc_fence_after();
-    }
-    if (clus) { cluster_arrive_release(); cluster_wait_acquire(); }   // barrier #1: the peer's partial is visible
-    if (warp == 2 && lane == 0) { DQNB_STAMP(4); DQNB_STAMP_MAX(9); }
-    const float *peer_row = st_hi + lane * LDS;          // same offset inside the peer CTA's shared memory
-    const uint32_t box0 = base + (uint32_t)(q * NCH) * 8192u;   // this warp's staging boxes: [chunk][plane][32 rows][128 B]
-    const uint32_t row_off = (uint32_t)lane * 128u, sw = (uint32_t)(lane & 7);
-    const int planes_out = p.epi == EPI_PLAIN ? 1 : 2;
-    // column chunks of 32: the TMEM loads of chunk c+1 are in flight while chunk c is processed
-    uint32_t ra[2][32], rb[2][32];
-    const uint32_t taddr0 = tmem + ((uint32_t)(q * 32) << 16);
-    if (iters > 0) { tmem_ld32(taddr0, ra[0]); tmem_ld32(taddr0 + BN_, rb[0]); }
-#pragma unroll
-    for (int c0 = 0; c0 < BN_; c0 += 32) {
-      float v[32];
-      constexpr int kLast = BN_ - 32;
-      const int cur = (c0 >> 5) & 1;
-      const uint32_t bits_in = rbits[c0 / 32];
-      uint32_t bits_out = 0u;
-      if (iters > 0) {
-        tmem_wait_ld();
-        if (c0 < kLast) { tmem_ld32(taddr0 + (uint32_t)(c0 + 32), ra[cur ^ 1]); tmem_ld32(taddr0 + (uint32_t)(c0 + 32) + BN_, rb[cur ^ 1]); }
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(ra[cur][j]) + __uint_as_float(rb[cur][j]);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = 0.f;
-      }
-      if (clus) {                            // + the other half of K, from the peer CTA's shared memory
-        const uint32_t mine = smem_u32(peer_row + c0);
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 pp = ld_dsmem_f4(mine + j * 4, 1u);
-          v[j] += pp.x; v[j + 1] += pp.y; v[j + 2] += pp.z; v[j + 3] += pp.w;
-        }
-      }
-      const uint32_t box = box0 + (uint32_t)(c0 >> 5) * 8192u + row_off;
-      if (p.epi == EPI_PLAIN) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          st_smem_f4(box + ((((uint32_t)j >> 2) ^ sw) << 4), v[j], v[j + 1], v[j + 2], v[j + 3]);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float o[4], l[4];
-          float4 aux = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.epi == EPI_FWD) aux = *reinterpret_cast<const float4 *>(s_bias + c0 + j);
-          const float ax[4] = {aux.x, aux.y, aux.z, aux.w};
-#pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            float x = v[j + t];
-            if (p.epi == EPI_FWD) {
-              x += ax[t];                                            // InnerProduct bias
-              if (p.apply_lrelu) x = fmaxf(x, 0.f) + kNegSlope * fminf(x, 0.f);
-              bits_out |= (x > 0.f ? 1u : 0u) << (j + t);            // sign of the in-place activation
-            } else {
-              x *= ((bits_in >> (j + t)) & 1u) ? 1.f : kNegSlope;    // ReLU backward on the in-place activation
-            }
-            o[t] = tf32_hi(x);
-            l[t] = x - o[t];
+      for (int i = 0; i < MYCH; ++i) {
+        const int c0 = (half + 2 * i) * 32;
+        const int cur = i & 1;
+        float v[32];
+        const uint32_t bits_in = rbits[i];
+        uint32_t bits_out = 0u;
+        if (iters > 0) {
+          tmem_wait_ld();
+          if (i + 1 < MYCH) {              // next chunk in flight while this one is processed
+            tmem_ld32(taddr0 + (uint32_t)(c0 + 64), ra[cur ^ 1]);
+            tmem_ld32(taddr0 + (uint32_t)(c0 + 64) + BN_, rb[cur ^ 1]);
           }
-          const uint32_t slot = box + ((((uint32_t)j >> 2) ^ sw) << 4);
-          st_smem_f4(slot, o[0], o[1], o[2], o[3]);
-          st_smem_f4(slot + 4096u, l[0], l[1], l[2], l[3]);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(ra[cur][j]) + __uint_as_float(rb[cur][j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0.f;
         }
-        if (p.epi == EPI_FWD && p.relu_bits_out && m_row < p.M && n_base + c0 < p.N)
-          p.relu_bits_out[(long long)m_row * p.ldbits + ((n_base + c0) >> 5)] = bits_out;
+        if (clus) {                            // + the other half of K, from the peer CTA's shared memory
+          const uint32_t mine = smem_u32(peer_row + c0);
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 pp = ld_dsmem_f4(mine + j * 4, 1u);
+            v[j] += pp.x; v[j + 1] += pp.y; v[j + 2] += pp.z; v[j + 3] += pp.w;
+          }
+        }
+        const uint32_t box = box0 + (uint32_t)(c0 >> 5) * 8192u + row_off;
+        if (p.epi == EPI_PLAIN) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            st_smem_f4(box + ((((uint32_t)j >> 2) ^ sw) << 4), v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float o[4], l[4];
+            float4 aux = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.epi == EPI_FWD) aux = *reinterpret_cast<const float4 *>(s_bias + c0 + j);
+            const float ax[4] = {aux.x, aux.y, aux.z, aux.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              float x = v[j + t];
+              if (p.epi == EPI_FWD) {
+                x += ax[t];                                            // InnerProduct bias
+                if (p.apply_lrelu) x = fmaxf(x, 0.f) + kNegSlope * fminf(x, 0.f);
+                bits_out |= (x > 0.f ? 1u : 0u) << (j + t);            // sign of the in-place activation
+              } else {
+                x *= ((bits_in >> (j + t)) & 1u) ? 1.f : kNegSlope;    // ReLU backward on the in-place activation
+              }
+              o[t] = tf32_hi(x);
+              l[t] = x - o[t];
+            }
+            const uint32_t slot = box + ((((uint32_t)j >> 2) ^ sw) << 4);
+            st_smem_f4(slot, o[0], o[1], o[2], o[3]);
+            st_smem_f4(slot + 4096u, l[0], l[1], l[2], l[3]);
+          }
+          if (p.epi == EPI_FWD && p.relu_bits_out && m_row < p.M && n_base + c0 < p.N)
+            p.relu_bits_out[(long long)m_row * p.ldbits + ((n_base + c0) >> 5)] = bits_out;
+        }
+        // hand this chunk's box (both planes) to the TMA unit; the next chunk is staged meanwhile
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0 && n_base + c0 < p.N && m_tile * BM + q * 32 < p.M) {
+          tma_store_3d(&args.tmD, box - row_off, n_base + c0, m_tile * BM + q * 32, planes_out == 1 ? split : 0);
+          bulk_commit();
+        }
       }
-      // hand this chunk's box (both planes) to the TMA unit; the next chunk is staged meanwhile
-      fence_proxy_async_smem();
+      if (lane == 0) bulk_wait_all();          // the boxes have been read and written before shared memory goes away
       __syncwarp();
-      if (lane == 0 && n_base + c0 < p.N && m_tile * BM + q * 32 < p.M) {
-        tma_store_3d(&args.tmD, box - row_off, n_base + c0, m_tile * BM + q * 32, planes_out == 1 ? split : 0);
-        bulk_commit();
-      }
+      if (warp == 2 && lane == 0) { DQNB_STAMP(5); DQNB_STAMP_MAX(10); }
     }
-    if (lane == 0) bulk_wait_all();          // the boxes have been read and written before shared memory goes away
-    __syncwarp();
-    if (warp == 2 && lane == 0) { DQNB_STAMP(5); DQNB_STAMP_MAX(10); }
-    }   // !(cluster peer)
   }
   if (clus) {
     // every thread of both CTAs passes two cluster barriers: #1 publishes the peer's partial tile (the
-    // leader's epilogue warps already passed it above), #2 keeps the peer's shared memory alive until the
-    // leader has read it
-    if (!(warp >= 2 && crank == 0)) { cluster_arrive_release(); cluster_wait_acquire(); }
+    // leader's warps already passed it above), #2 keeps the peer's shared memory alive until the leader
+    // has read it
+    if (crank != 0) { cluster_arrive_release(); cluster_wait_acquire(); }
     cluster_arrive_release();
     cluster_wait_acquire();
   }
