@@ -10,7 +10,9 @@ per GPU drawn from an HBM-resident replay ring of synthetic 58-dim transitions.
 
 `value`   : device-timed (CUDA events on the handle's stream), replay already resident in HBM.
 `e2e`     : the same metric through the C-ABI with HOST buffers every step: dqnb_add_transitions of B
-            fresh rows (H2D) + dqnb_update (1 update) + read back (critic_loss, avg_q) (D2H).
+            fresh rows (pinned staging -> H2D on the copy stream) + dqnb_update_async (1 update) + the
+            previous step's (critic_loss, avg_q) read from the host-mapped result ring (dqnb_results);
+            `blocking_value` is the same loop with the blocking dqnb_update.
 `roofline`: the dominant kernel (gemm_tc_kernel, tcgen05 3xTF32) timed live with CUDA events.
 `cpu_baseline`: the oracle port (Caffe operation order, OpenBLAS sgemm when loadable) on a bounded sample.
 """
@@ -290,22 +292,43 @@ def main():
     value = B * world * args.steps / (ms_max * 1e-3)
 
     # ---- e2e through the C-ABI with host buffers ----------------------------------------------
+    # Every step: B fresh host rows -> pinned staging -> H2D into the ring (dqnb_add_transitions), one
+    # update (dqnb_update_async), and the (critic_loss, avg_q) of the previous step read back from the
+    # host-mapped result ring (dqnb_results) while the current one runs - the learner loop of a caller
+    # that logs its loss one step late.  All results are in host memory when the clock stops.  The
+    # strictly blocking variant (dqnb_update returns the loss of the same step) is reported beside it.
     e2e_steps = min(args.steps, 500)
     fresh = synth_replay(B * 8, S, seed=100 + rank)
+
+    def add_rows(k):
+        o = (k % 8) * B
+        d.add_transitions(fresh[0][o:o + B], fresh[1][o:o + B], fresh[2][o:o + B], fresh[3][o:o + B],
+                          fresh[5][o:o + B], fresh[4][o:o + B])
+
     d.update(3)
     barrier()
     t0 = time.perf_counter()
     for k in range(e2e_steps):
-        o = (k % 8) * B
-        d.add_transitions(fresh[0][o:o + B], fresh[1][o:o + B], fresh[2][o:o + B], fresh[3][o:o + B],
-                          fresh[5][o:o + B], fresh[4][o:o + B])
+        add_rows(k)
         loss, avgq = d.update(1)
     d.sync()
+    dt_sync = time.perf_counter() - t0
+    barrier()
+    t0 = time.perf_counter()
+    step = 0
+    for k in range(e2e_steps):
+        add_rows(k)
+        step = d.update_async(1)
+        if k > 0:
+            loss, avgq = d.results(step - 1, 1)
+    loss, avgq = d.results(step, 1)
+    d.sync()
     dt = time.perf_counter() - t0
-    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    t = torch.tensor([dt, dt_sync], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_val = B * world * e2e_steps / float(t.item())
+    e2e_val = B * world * e2e_steps / float(t[0].item())
+    e2e_sync_val = B * world * e2e_steps / float(t[1].item())
     Sp = (S + 63) // 64 * 64
     h2d = B * (2 * Sp + 16) * 4 + 8 + 4
     d2h = 8
@@ -316,7 +339,9 @@ def main():
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (3xTF32 tensor-core products, fp32 accumulate)",
         "data": "synthetic", "config": workload_config(args, world), "clocks": sampler.result(),
         "e2e": {"value": e2e_val, "unit": "transitions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps, "what": "dqnb_add_transitions(B host rows) + dqnb_update(1) + read (critic_loss, avg_q)"},
+                "steps": e2e_steps, "blocking_value": e2e_sync_val,
+                "what": "per step: dqnb_add_transitions(B host rows -> pinned -> H2D on the copy stream) + dqnb_update_async(1) + "
+                        "dqnb_results of the previous step (host-mapped result ring); blocking_value = same loop with dqnb_update(1)"},
         "gpu_launches": int(launches),
         "final": {"critic_loss": float(loss[-1]), "avg_q": float(avgq[-1])},
     }

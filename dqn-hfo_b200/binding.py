@@ -77,6 +77,8 @@ def lib():
     L.dqnb_get_transitions.argtypes = [H, C.c_int32, C.c_int32, fp, fp, fp, fp, fp, u8p]
     L.dqnb_update.argtypes = [H, C.c_int32, fp, fp]
     L.dqnb_update_with_indices.argtypes = [H, ip, fp, fp]
+    L.dqnb_update_async.argtypes = [H, C.c_int32, C.POINTER(C.c_int64)]
+    L.dqnb_results.argtypes = [H, C.c_int64, C.c_int32, fp, fp]
     L.dqnb_benchmark.argtypes = [H, C.c_int32, fp]
     L.dqnb_benchmark_gemms.argtypes = [H, C.c_int32, fp, ip]
     L.dqnb_peek_sample_indices.argtypes = [H, ip]
@@ -104,7 +106,7 @@ EXPORTS = [
     "dqnb_param_count", "dqnb_set_params", "dqnb_get_params", "dqnb_init_params", "dqnb_clone_targets",
     "dqnb_set_opt_state", "dqnb_get_opt_state", "dqnb_iters", "dqnb_add_transitions",
     "dqnb_add_transition", "dqnb_memory_size", "dqnb_clear_memory", "dqnb_get_transitions",
-    "dqnb_update", "dqnb_update_with_indices", "dqnb_benchmark", "dqnb_benchmark_gemms",
+    "dqnb_update", "dqnb_update_async", "dqnb_results", "dqnb_update_with_indices", "dqnb_benchmark", "dqnb_benchmark_gemms",
     "dqnb_peek_sample_indices",
     "dqnb_select_actions", "dqnb_select_actions_async", "dqnb_select_actions_wait", "dqnb_evaluate",
     "dqnb_comm_unique_id", "dqnb_comm_init", "dqnb_comm_p2p_handle", "dqnb_comm_p2p_init", "dqnb_comm_status",
@@ -253,6 +255,17 @@ class DQNB:
     def update(self, n=1):
         loss, avgq = np.zeros(n, np.float32), np.zeros(n, np.float32)
         _check(lib().dqnb_update(self._h, n, _f(loss), _f(avgq)))
+        return loss, avgq
+
+    def update_async(self, n=1):
+        """Enqueue n updates; returns the 1-based sequence number of the last one (see results())."""
+        last = C.c_int64(0)
+        _check(lib().dqnb_update_async(self._h, n, C.byref(last)))
+        return int(last.value)
+
+    def results(self, first_step, n=1):
+        loss, avgq = np.zeros(n, np.float32), np.zeros(n, np.float32)
+        _check(lib().dqnb_results(self._h, first_step, n, _f(loss), _f(avgq)))
         return loss, avgq
 
     def update_with_indices(self, idx):

@@ -221,6 +221,8 @@ static void internal_to_caffe(const NetGeom &g, const float *in, float *c) {
 }
 
 // ---------------------------------------------------------------------------------------------
+constexpr int kMaxSide = 2 + DQNB_MAX_HIDDEN;
+
 struct SplitMat {           // [2][rows][ld] fp32 in HBM
   float *p = nullptr;
   uint32_t *bits = nullptr; // optional [rows][ld/32]: ReLU sign bits of a saved activation (gemm.cuh relu_bits_*)
@@ -253,8 +255,10 @@ struct dqnb_handle_s {
   int S, Sp, Kc, B, Bp, An /*act rows pad*/;
   NetGeom gA, gC;
   cudaStream_t stream = nullptr;
-  cudaStream_t side[2] = {nullptr, nullptr};          // independent forward chains run beside the main one
-  cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+  // side streams -> parallel branches of the captured graph.  0, 1: independent forward chains / head gradients;
+  // 2 + l: the weight-gradient GEMM of tower layer l (each starts as soon as its dZ exists)
+  cudaStream_t side[kMaxSide] = {};
+  cudaEvent_t ev_fork = nullptr, ev_join[kMaxSide] = {};
   cudaEvent_t evs[8] = {};                            // cross-branch edges inside one update
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::vector<void *> allocs;
@@ -295,7 +299,17 @@ struct dqnb_handle_s {
   float *h_results = nullptr;       // mapped pinned ring the last optimiser launch writes (critic_loss, avg_q) into
   unsigned long long host_step = 0;  // updates enqueued so far (mirrors StepState::step)
   // staging for replay appends
-  float *h_stage = nullptr; int stage_rows = 0;   // pinned staging rows in ring layout (padding stays zero)
+  // Replay appends travel on their own copy stream, beside the running update: pinned staging slots (ring
+  // layout, padding stays zero; the slot's last 16 bytes carry {head, size}) -> H2D straight into the ring.
+  // Ordering: a copy waits for the last enqueued gather (the only reader of the ring), the next gather waits
+  // for the copy.
+  static constexpr int kStageSlots = 2;
+  float *h_stage[kStageSlots] = {nullptr, nullptr}; int stage_rows = 0; int stage_next = 0;
+  cudaEvent_t ev_stage[kStageSlots] = {nullptr, nullptr};   // H2D copies out of a slot are done
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_copy = nullptr, ev_gather = nullptr;
+  bool copy_pending = false;          // the compute stream has not yet been ordered after the last append
+  volatile unsigned long long *h_done = nullptr; unsigned long long *d_done = nullptr;   // mapped: last finished update
   // op lists + graphs
   std::vector<Op> update_ops, act_ops, eval_ops;
   cudaGraphExec_t graph_sampled = nullptr, graph_injected = nullptr;
@@ -345,15 +359,22 @@ struct Tuning {
   int sched;        // 0: three forward chains at once; 1: (target actor || critic) then (target critic || actor)
   int dw0_main;     // 1: the last weight-gradient GEMM (layer 0) follows the dX chain on the main stream
   int colsum_side;  // 1: bias column sums on side stream 1 beside that GEMM
+  int dw_streams;   // 1: every weight-gradient GEMM on its own side stream, per-layer bias column sums on stream 2
   int bn_fwd, bn_fwd_side, bn_dx, bn_dw;   // N tile (64 / 128) per GEMM class
+  int st_fwd, st_fwd_side, st_dx, st_dw;   // smem ring depth per GEMM class (0 = deepest that fits)
   Tuning() {
     sched = env_int("DQNB_SCHED", 0);
     dw0_main = env_int("DQNB_DW0_MAIN", 0);
     colsum_side = env_int("DQNB_COLSUM_SIDE", 0);
+    dw_streams = env_int("DQNB_DW_STREAMS", 1);
     bn_fwd = env_int("DQNB_BN_FWD", 64);
     bn_fwd_side = env_int("DQNB_BN_FWD_SIDE", 64);
     bn_dx = env_int("DQNB_BN_DX", 64);
     bn_dw = env_int("DQNB_BN_DW", 64);
+    st_fwd = env_int("DQNB_ST_FWD", 0);
+    st_fwd_side = env_int("DQNB_ST_FWD_SIDE", 0);
+    st_dx = env_int("DQNB_ST_DX", 0);
+    st_dw = env_int("DQNB_ST_DW", 2);   // two weight-gradient CTAs per SM: -2.4% per update (measured)
   }
 };
 static const Tuning &tuning() {
@@ -378,6 +399,7 @@ static int finish_gemm(const dqnb_config &cfg, Op *op) {
     // A
     const int a_rows = p.a_mn ? p.K : p.M, b_rows = p.b_mn ? p.K : p.N;
     if (p.bn != 64 && p.bn != 128) p.bn = 64;
+    if (p.stages < 2 || p.stages > tc_max_stages(p.bn)) p.stages = tc_max_stages(p.bn);
     if (p.epi == EPI_DX && !p.relu_bits_in) DQNB_FAIL("EPI_DX needs the sign bits of the saved activation");
     // Forward / dX GEMMs with a long contraction but few output tiles: split K over a 2-CTA cluster
     // (DSMEM reduction in the epilogue) so that the dependent chain sees half the mainloop latency.
@@ -405,11 +427,12 @@ static int finish_gemm(const dqnb_config &cfg, Op *op) {
 
 // forward of tower layer l: H = lrelu(X W^T + b)
 static int op_fwd(const dqnb_config &cfg, const NetGeom &g, int l, const float *P, const SplitMat &X,
-                  const SplitMat &H, Op *op, int bn = 64) {
+                  const SplitMat &H, Op *op, int bn = 64, int stages = 0) {
   const LayerGeom &L = g.L[l];
   GemmParams &p = op->gemm.p;
   memset(&p, 0, sizeof(p));
   p.bn = (bn == 128 && L.Np % 128 == 0) ? 128 : 64;
+  p.stages = stages;
   p.M = X.rows; p.N = L.Np; p.K = L.Kp; p.a_mn = 0; p.b_mn = 0; p.splits = 1; p.epi = EPI_FWD;
   p.A = X.p; p.a_plane = X.plane(); p.lda = X.ld;
   p.B = P + L.w_off; p.b_plane = g.flat; p.ldb = L.Kp;
@@ -425,6 +448,7 @@ static int op_dx(const dqnb_config &cfg, const NetGeom &g, int l, const float *P
   GemmParams &p = op->gemm.p;
   memset(&p, 0, sizeof(p));
   p.bn = (tuning().bn_dx == 128 && L.Kp % 128 == 0) ? 128 : 64;
+  p.stages = tuning().st_dx;
   p.M = dZl.rows; p.N = L.Kp; p.K = L.Np; p.a_mn = 0; p.b_mn = 1; p.splits = 1; p.epi = EPI_DX;
   p.A = dZl.p; p.a_plane = dZl.plane(); p.lda = dZl.ld;
   p.B = P + L.w_off; p.b_plane = g.flat; p.ldb = L.Kp;
@@ -457,6 +481,7 @@ static int op_dw(const dqnb_config &cfg, const NetGeom &g, int l, const SplitMat
   memset(&p, 0, sizeof(p));
   p.M = L.Np; p.N = L.Kp; p.K = dZl.rows; p.a_mn = 1; p.b_mn = 1; p.epi = EPI_PLAIN;
   p.bn = (tuning().bn_dw == 128 && L.Kp % 128 == 0) ? 128 : 64;
+  p.stages = tuning().st_dw;
   const int tiles = ((p.M + BM - 1) / BM) * ((p.N + p.bn - 1) / p.bn);
   p.splits = pick_splits(tiles, p.K / BK, kGradSplits);
   *splits_out = p.splits;
@@ -509,14 +534,14 @@ static int launch_op(dqnb_handle_s *h, const Op &op, cudaStream_t s) {
       if (h->cfg.gemm_mode == DQNB_GEMM_TCGEN05_3XTF32) {
         g_cluster_z = op.gemm.p.cluster_k ? 2 : 1;
         e = launch_k(tc_kernel_for(op.gemm.p.a_mn, op.gemm.p.b_mn, op.gemm.p.bn), op.grid, dim3(TC_THREADS),
-                     (size_t)tc_smem_for(op.gemm.p.bn), s, op.gemm);
+                     (size_t)tc_smem_for(op.gemm.p.bn, op.gemm.p.stages), s, op.gemm);
         g_cluster_z = 1;
       }
       else
         e = launch_k(gemm_simt_kernel, op.grid, dim3(256), 0, s, op.gemm.p);
       break;
     case Op::GEMM_GROUP:
-      e = launch_k(gemm_tc_grouped_kernel<1, 1, 64>, op.grid, dim3(TC_THREADS), (size_t)tc_smem_for(64), s, op.group);
+      e = launch_k(gemm_tc_grouped_kernel<1, 1, 64>, op.grid, dim3(TC_THREADS), (size_t)tc_smem_for(64, tc_max_stages(64)), s, op.group);
       break;
     case Op::GATHER: e = launch_k(gather_kernel, dim3(h->Bp), dim3(128), 0, s, op.gather); break;
     case Op::SAMPLE:
@@ -554,14 +579,15 @@ static int run_ops(dqnb_handle_s *h, const std::vector<Op> &ops, cudaStream_t s,
   int n = 0;
   for (const Op &op : ops) {
     if (op.variant == (skip_sample ? 1 : 2)) continue;
+    if (op.kind == Op::GATHER) continue;       // launched by enqueue_update ahead of the graph
     if (op.kind == Op::FORK) {          // side streams pick up after everything queued on the main one
       DQNB_CUDA(cudaEventRecord(h->ev_fork, s));
-      for (int b = 0; b < 2; ++b)
+      for (int b = 0; b < kMaxSide; ++b)
         if (op.mask & (1 << b)) DQNB_CUDA(cudaStreamWaitEvent(h->side[b], h->ev_fork, 0));
       continue;
     }
     if (op.kind == Op::JOIN) {
-      for (int b = 0; b < 2; ++b)
+      for (int b = 0; b < kMaxSide; ++b)
         if (op.mask & (1 << b)) {
           DQNB_CUDA(cudaEventRecord(h->ev_join[b], h->side[b]));
           DQNB_CUDA(cudaStreamWaitEvent(s, h->ev_join[b], 0));
@@ -586,7 +612,8 @@ static int build_forward(dqnb_handle_s *h, const NetGeom &g, const float *P, con
   const SplitMat *in = &X;
   for (int l = 0; l < g.n_hidden; ++l) {
     Op op;
-    if (op_fwd(h->cfg, g, l, P, *in, acts[l], &op, critical_chain ? tuning().bn_fwd : tuning().bn_fwd_side)) return -1;
+    if (op_fwd(h->cfg, g, l, P, *in, acts[l], &op, critical_chain ? tuning().bn_fwd : tuning().bn_fwd_side,
+               critical_chain ? tuning().st_fwd : tuning().st_fwd_side)) return -1;
     if (!critical_chain && op.gemm.p.cluster_k) {
       // side-branch passes run beside the critical chain: they should not grab twice the SMs for a
       // latency that nobody waits on, so they keep one CTA per tile
@@ -598,26 +625,48 @@ static int build_forward(dqnb_handle_s *h, const NetGeom &g, const float *P, con
   return 0;
 }
 
+// bias gradients (column sums of dZ) of tower layers [l0, l1)
+static Op make_colsum(dqnb_handle_s *h, const NetGeom &g, int l0, int l1) {
+  Op op;
+  op.kind = Op::COLSUM;
+  ColsumArgs &a = op.cs;
+  memset(&a, 0, sizeof(a));
+  a.n_layers = l1 - l0; a.rows_pad = h->Bp;
+  int blk = 0;
+  for (int l = l0; l < l1; ++l) {
+    const int i = l - l0;
+    a.dZ[i] = h->dZ[l].p; a.plane[i] = h->dZ[l].plane(); a.ld[i] = h->dZ[l].ld; a.Np[i] = g.L[l].Np;
+    a.b_off[i] = g.L[l].b_off; a.blk_begin[i] = blk; blk += (g.L[l].Np + 127) / 128;
+  }
+  a.blk_begin[l1 - l0] = blk;
+  a.gpart = h->Gpart[g.critic]; a.gpart_stride = h->gpart_stride[g.critic];
+  op.grid = dim3(blk, kGradSplits);
+  return op;
+}
+
 // tower backward from dZ[top] (already masked by the head backward).  The dX chain is the critical
-// path and stays on the main stream; with want_dw the weight-gradient GEMMs, the head gradients and the
-// bias column sums run on side stream 1, each gated by an event on the dZ it consumes, and JOIN back
-// before the gradient reduction.
+// path and stays on the main stream.  With want_dw every weight-gradient GEMM runs on a side stream of its
+// own (side 2 + l) and the head gradient + per-layer bias column sums on side 1, each gated by an event on
+// the dZ it consumes, so a gradient starts the moment its dZ exists; all JOIN back before the reduction.
 static int build_backward(dqnb_handle_s *h, const NetGeom &g, const float *P, const SplitMat &X,
                           SplitMat *acts, bool want_dw, SegTable *segs, const Op *head_bwd_w,
                           std::vector<Op> &ops) {
   const int top = g.n_hidden - 1;
   if (g.n_hidden + 1 > 8) DQNB_FAIL("too many layers for the event table");
+  const bool grouped_env = getenv("DQNB_GROUPED_DW") != nullptr;
+  const bool dws = want_dw && tuning().dw_streams && !grouped_env;
+  int fork_mask = 3;
+  if (dws) for (int l = 0; l <= top; ++l) fork_mask |= 1 << (2 + l);
   if (want_dw) {
-    // both side streams pick up once dZ[top] exists: side 1 runs the per-layer weight-gradient GEMMs, side 2
-    // the head weight/bias gradient, so neither delays the other
-    Op f; f.kind = Op::FORK; f.mask = 3; ops.push_back(f);
+    // the side streams pick up once dZ[top] exists
+    Op f; f.kind = Op::FORK; f.mask = fork_mask; ops.push_back(f);
     if (head_bwd_w) { Op w = *head_bwd_w; w.branch = 2; ops.push_back(w); }
+    if (dws) { Op c = make_colsum(h, g, top, top + 1); c.branch = 2; ops.push_back(c); }
   }
   // Experiment kept behind DQNB_GROUPED_DW=1: the weight-gradient GEMMs of all layers as ONE grouped launch
   // after the dX chain.  Measured 2.75e6 vs 2.75-2.79e6 tr/s for the per-layer launches that overlap the
   // chain on the side stream (the group is ~3 waves of CTAs that only start when the chain is done).
-  const bool grouped = want_dw && h->cfg.gemm_mode == DQNB_GEMM_TCGEN05_3XTF32 && g.n_hidden <= kMaxGroup &&
-                       getenv("DQNB_GROUPED_DW") != nullptr;
+  const bool grouped = want_dw && h->cfg.gemm_mode == DQNB_GEMM_TCGEN05_3XTF32 && g.n_hidden <= kMaxGroup && grouped_env;
   Op grp;
   grp.kind = Op::GEMM_GROUP;
   grp.group.n = 0;
@@ -627,7 +676,7 @@ static int build_backward(dqnb_handle_s *h, const NetGeom &g, const float *P, co
       Op op;
       int splits = 1;
       if (op_dw(h->cfg, g, l, h->dZ[l], l > 0 ? acts[l - 1] : X, h->Gpart[g.critic], h->gpart_stride[g.critic], &splits, &op)) return -1;
-      op.branch = 1;
+      op.branch = dws ? 3 + l : 1;
       if (l < top) op.wait_ev = l;                              // dZ[l] is produced by the dX op below
       if (l == 0 && top > 0 && tuning().dw0_main && !grouped) {
         // the last weight gradient only waits for the dX op right before it: on the main stream it starts with a
@@ -651,6 +700,7 @@ static int build_backward(dqnb_handle_s *h, const NetGeom &g, const float *P, co
       if (op_dx(h->cfg, g, l, P, h->dZ[l], acts[l - 1], h->dZ[l - 1], &op)) return -1;
       if (want_dw) op.rec_ev = l - 1;                           // dZ[l-1] ready
       ops.push_back(op);
+      if (dws) { Op c = make_colsum(h, g, l - 1, l); c.branch = 2; c.wait_ev = l - 1; ops.push_back(c); }
     }
   }
   if (grouped) {
@@ -660,26 +710,16 @@ static int build_backward(dqnb_handle_s *h, const NetGeom &g, const float *P, co
     ops.push_back(grp);
   }
   if (want_dw) {
-    Op op;
-    op.kind = Op::COLSUM;                                       // main stream: every dZ exists after the dX chain
-    ColsumArgs &a = op.cs;
-    memset(&a, 0, sizeof(a));
-    a.n_layers = g.n_hidden; a.rows_pad = h->Bp;
-    int blk = 0;
-    for (int l = 0; l < g.n_hidden; ++l) {
-      a.dZ[l] = h->dZ[l].p; a.plane[l] = h->dZ[l].plane(); a.ld[l] = h->dZ[l].ld; a.Np[l] = g.L[l].Np;
-      a.b_off[l] = g.L[l].b_off; a.blk_begin[l] = blk; blk += (g.L[l].Np + 127) / 128;
+    if (!dws) {
+      Op op = make_colsum(h, g, 0, g.n_hidden);                 // main stream: every dZ exists after the dX chain
+      if (tuning().colsum_side && top > 0) { op.branch = 1; op.wait_ev = 0; }   // beside the layer-0 weight gradient
+      ops.push_back(op);
     }
-    a.blk_begin[g.n_hidden] = blk;
-    a.gpart = h->Gpart[g.critic]; a.gpart_stride = h->gpart_stride[g.critic];
-    op.grid = dim3(blk, kGradSplits);
-    if (tuning().colsum_side && top > 0) { op.branch = 1; op.wait_ev = 0; }   // beside the layer-0 weight gradient
-    ops.push_back(op);
     SegTable &T = *segs;
     const int hs = 2 * g.n_hidden;
     T.begin[hs] = g.hw_off; T.end[hs] = g.flat; T.nsplit[hs] = kGradSplits;   // head W, b (+ zero tail)
     T.n = hs + 1;
-    Op j; j.kind = Op::JOIN; j.mask = 3; ops.push_back(j);
+    Op j; j.kind = Op::JOIN; j.mask = fork_mask; ops.push_back(j);
   }
   return 0;
 }
@@ -853,7 +893,7 @@ static int build_update_ops(dqnb_handle_s *h) {
   {   // the last optimiser launch also publishes (critic_loss, avg_q) and advances the counters
     AdamArgs &d = ops.back().adam;
     d.finalize = 1; d.ticket = h->ticket; d.g_critic_tail = h->Gr[1] + gC.flat; d.g_actor_tail = h->Gr[0] + gA.flat;
-    d.results = h->results; d.max_slots = h->max_slots;
+    d.results = h->results; d.max_slots = h->max_slots; d.done = h->d_done;
   }
   return 0;
 }
@@ -928,7 +968,7 @@ int dqnb_destroy(dqnb_handle h) {
   for (void *p : h->ipc_opened) cudaIpcCloseMemHandle(p);
   for (void *p : h->allocs) cudaFree(p);
   for (void *p : h->pinned) cudaFreeHost(p);
-  for (int b = 0; b < 2; ++b) {
+  for (int b = 0; b < kMaxSide; ++b) {
     if (h->ev_join[b]) cudaEventDestroy(h->ev_join[b]);
     if (h->side[b]) cudaStreamDestroy(h->side[b]);
   }
@@ -936,6 +976,10 @@ int dqnb_destroy(dqnb_handle h) {
   for (int i = 0; i < 8; ++i) if (h->evs[i]) cudaEventDestroy(h->evs[i]);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
+  for (int i = 0; i < dqnb_handle_s::kStageSlots; ++i) if (h->ev_stage[i]) cudaEventDestroy(h->ev_stage[i]);
+  if (h->ev_copy) cudaEventDestroy(h->ev_copy);
+  if (h->ev_gather) cudaEventDestroy(h->ev_gather);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return 0;
@@ -965,7 +1009,12 @@ static int create_impl(const dqnb_config *cfg, dqnb_handle_s *h) {
   DQNB_CUDA(cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prio_hi));
   DQNB_CUDA(cudaEventCreate(&h->ev0));
   DQNB_CUDA(cudaEventCreate(&h->ev1));
-  for (int b = 0; b < 2; ++b) {
+  DQNB_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < dqnb_handle_s::kStageSlots; ++i) DQNB_CUDA(cudaEventCreateWithFlags(&h->ev_stage[i], cudaEventDisableTiming));
+  DQNB_CUDA(cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming));
+  DQNB_CUDA(cudaEventCreateWithFlags(&h->ev_gather, cudaEventDisableTiming));
+  DQNB_CUDA(cudaEventRecord(h->ev_gather, h->stream));
+  for (int b = 0; b < kMaxSide; ++b) {
     DQNB_CUDA(cudaStreamCreateWithPriority(&h->side[b], cudaStreamNonBlocking, prio_lo));
     DQNB_CUDA(cudaEventCreateWithFlags(&h->ev_join[b], cudaEventDisableTiming));
   }
@@ -1035,7 +1084,16 @@ static int create_impl(const dqnb_config *cfg, dqnb_handle_s *h) {
     h->h_results = (float *)hp; h->results = (float *)dp;
   }
   h->stage_rows = 4096;
-  if (halloc(h, &h->h_stage, (size_t)h->stage_rows * h->rw)) return -1;
+  for (int i = 0; i < dqnb_handle_s::kStageSlots; ++i)
+    if (halloc(h, &h->h_stage[i], (size_t)h->stage_rows * h->rw + 4)) return -1;
+  {   // update counter the last optimiser launch publishes for the host (dqnb_results polls it)
+    void *hp = nullptr, *dp = nullptr;
+    DQNB_CUDA(cudaHostAlloc(&hp, 64, cudaHostAllocMapped));
+    memset(hp, 0, 64);
+    h->pinned.push_back(hp);
+    DQNB_CUDA(cudaHostGetDevicePointer(&dp, hp, 0));
+    h->h_done = (volatile unsigned long long *)hp; h->d_done = (unsigned long long *)dp;
+  }
   if (build_update_ops(h) || build_act_ops(h)) return -1;
   if (getenv("DQNB_TRACE")) {
     h->trace_ops = (int)h->update_ops.size() + 16;   // head room: the op list grows when a communicator is attached
@@ -1139,8 +1197,9 @@ static int upload_flat(dqnb_handle h, const NetGeom &g, const float *caffe, floa
   return 0;
 }
 
+static int sync_all(dqnb_handle h);
 static int pull_state(dqnb_handle h, StepState *s) {
-  DQNB_CUDA(cudaStreamSynchronize(h->stream));
+  if (sync_all(h)) return -1;
   DQNB_CUDA(cudaMemcpy(s, h->st, sizeof(StepState), cudaMemcpyDeviceToHost));
   return 0;
 }
@@ -1187,10 +1246,25 @@ int dqnb_iters(dqnb_handle h, int32_t *actor_iter, int32_t *critic_iter) {
 }
 
 // ----------------------------------- replay ring -----------------------------------------------
+// Everything queued on the copy stream happens before whatever the compute stream gets next.
+static int order_compute_after_copies(dqnb_handle h) {
+  if (h->copy_pending) {
+    DQNB_CUDA(cudaStreamWaitEvent(h->stream, h->ev_copy, 0));
+    h->copy_pending = false;
+  }
+  return 0;
+}
+static int sync_all(dqnb_handle h) {
+  DQNB_CUDA(cudaStreamSynchronize(h->copy_stream));
+  DQNB_CUDA(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
 static int push_ring_state(dqnb_handle h) {
-  // head/size live in StepState so the captured graph always sees the current ring
+  // head/size live in StepState so the captured graph always sees the current ring (rare path: blocking)
+  if (sync_all(h)) return -1;
   int hs[2] = {h->ring_head, h->ring_size};
-  DQNB_CUDA(cudaMemcpyAsync(&h->st->ring_head, hs, sizeof(hs), cudaMemcpyHostToDevice, h->stream));
+  DQNB_CUDA(cudaMemcpy(&h->st->ring_head, hs, sizeof(hs), cudaMemcpyHostToDevice));
   return 0;
 }
 
@@ -1200,10 +1274,13 @@ static int append_rows(dqnb_handle h, int32_t n, const float *s, const float *ac
   int done = 0;
   while (done < n) {
     const int chunk = std::min(n - done, h->stage_rows);
-    DQNB_CUDA(cudaStreamSynchronize(h->stream));   // the staging buffer is reused
+    const int slot = h->stage_next;
+    h->stage_next = (slot + 1) % dqnb_handle_s::kStageSlots;
+    DQNB_CUDA(cudaEventSynchronize(h->ev_stage[slot]));   // the copies out of this slot are done
+    float *stage = h->h_stage[slot];
     for (int i = 0; i < chunk; ++i) {              // padding columns of the staging rows are zero for good
       const int r = done + i;
-      float *row = h->h_stage + (size_t)i * rw;
+      float *row = stage + (size_t)i * rw;
       memcpy(row, s + (size_t)r * S, sizeof(float) * S);
       const bool t = terminal[r] != 0;
       if (!t && s_next) memcpy(row + Sp, s_next + (size_t)r * S, sizeof(float) * S); else memset(row + Sp, 0, sizeof(float) * S);
@@ -1211,17 +1288,25 @@ static int append_rows(dqnb_handle h, int32_t n, const float *s, const float *ac
       memcpy(dm, act10 + (size_t)r * kActorOut, sizeof(float) * kActorOut);
       dm[10] = reward[r]; dm[11] = mc[r]; dm[12] = t ? 1.f : 0.f;
     }
+    // the only reader of the ring (and of head/size) is the gather kernel of an update: wait for the last one queued
+    DQNB_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_gather, 0));
     int tail = (h->ring_head + h->ring_size) % cap;
     int left = chunk, src = 0;
     while (left > 0) {                              // one copy per contiguous run (two when the ring wraps)
       const int run = std::min(left, cap - tail);
-      DQNB_CUDA(cudaMemcpyAsync(h->ring + (size_t)tail * rw, h->h_stage + (size_t)src * rw, sizeof(float) * (size_t)run * rw, cudaMemcpyHostToDevice, h->stream));
+      DQNB_CUDA(cudaMemcpyAsync(h->ring + (size_t)tail * rw, stage + (size_t)src * rw, sizeof(float) * (size_t)run * rw, cudaMemcpyHostToDevice, h->copy_stream));
       tail = (tail + run) % cap; src += run; left -= run;
     }
     h->ring_size += chunk;
+    int *hs = reinterpret_cast<int *>(stage + (size_t)h->stage_rows * rw);
+    hs[0] = h->ring_head; hs[1] = h->ring_size;
+    DQNB_CUDA(cudaMemcpyAsync(&h->st->ring_head, hs, 2 * sizeof(int), cudaMemcpyHostToDevice, h->copy_stream));
+    DQNB_CUDA(cudaEventRecord(h->ev_stage[slot], h->copy_stream));
     done += chunk;
   }
-  return push_ring_state(h);
+  DQNB_CUDA(cudaEventRecord(h->ev_copy, h->copy_stream));
+  h->copy_pending = true;
+  return 0;
 }
 
 int dqnb_add_transitions(dqnb_handle h, int32_t n, const float *s, const float *act10, const float *reward,
@@ -1259,7 +1344,7 @@ int dqnb_get_transitions(dqnb_handle h, int32_t first, int32_t n, float *s, floa
                          float *mc_target, float *s_next, uint8_t *terminal) {
   if (!h || first < 0 || n < 0 || first + n > h->ring_size) DQNB_FAIL("bad range");
   DQNB_CUDA(cudaSetDevice(h->cfg.device));
-  DQNB_CUDA(cudaStreamSynchronize(h->stream));
+  if (sync_all(h)) return -1;
   const int cap = h->cfg.replay_capacity, S = h->S, Sp = h->Sp;
   const int rw = h->rw;
   std::vector<float> rows((size_t)n * rw);
@@ -1301,6 +1386,15 @@ static int ensure_graph(dqnb_handle h, bool injected) {
 static int enqueue_update(dqnb_handle h, bool injected) {
   h->host_step += 1;
   if (h->trace) DQNB_CUDA(cudaMemsetAsync(h->trace, 0xFF, sizeof(long long) * kTraceSlots * h->trace_ops, h->stream));
+  // The gather (dqn.cpp:846-887) is the one reader of the replay ring: it runs ahead of the captured graph so that
+  // an event can mark "ring consumed" for the copy stream (append_rows).
+  if (order_compute_after_copies(h)) return -1;
+  for (const Op &op : h->update_ops)
+    if (op.kind == Op::GATHER && op.variant == (injected ? 2 : 1)) {
+      if (launch_op(h, op, h->stream)) return -1;
+      h->launches += 1;
+    }
+  DQNB_CUDA(cudaEventRecord(h->ev_gather, h->stream));
   if (h->cfg.use_graph) {
     if (ensure_graph(h, injected)) return -1;
     DQNB_CUDA(cudaGraphLaunch(injected ? h->graph_injected : h->graph_sampled, h->stream));
@@ -1319,6 +1413,43 @@ static int fetch_results(dqnb_handle h, int n, float *critic_loss, float *avg_q)
   DQNB_CUDA(cudaStreamSynchronize(h->stream));
   for (int i = 0; i < n; ++i) {
     const int slot = (int)((h->host_step - (unsigned long long)n + i) % (unsigned long long)h->max_slots);
+    if (critic_loss) critic_loss[i] = h->h_results[2 * slot];
+    if (avg_q) avg_q[i] = h->h_results[2 * slot + 1];
+  }
+  return 0;
+}
+
+// Asynchronous pair: enqueue updates without waiting ...
+int dqnb_update_async(dqnb_handle h, int32_t n_updates, int64_t *last_step) {
+  if (!h || n_updates < 0) DQNB_FAIL("bad argument");
+  if (n_updates > 0 && h->ring_size <= 0) DQNB_FAIL("Update on an empty replay memory");
+  DQNB_CUDA(cudaSetDevice(h->cfg.device));
+  for (int i = 0; i < n_updates; ++i) if (enqueue_update(h, false)) return -1;
+  if (last_step) *last_step = (int64_t)h->host_step;
+  return 0;
+}
+
+// ... and collect (critic_loss, avg_q) of updates [first_step, first_step + n) (1-based sequence numbers as returned
+// by dqnb_update_async) once the last of them has finished.  The optimiser's final block publishes the results and
+// the number of finished updates in mapped pinned memory, so this is a spin on a host word, not a stream sync.
+int dqnb_results(dqnb_handle h, int64_t first_step, int32_t n, float *critic_loss, float *avg_q) {
+  if (!h || first_step < 1 || n < 0) DQNB_FAIL("bad argument");
+  if (n == 0) return 0;
+  const unsigned long long last = (unsigned long long)first_step + n - 1;
+  if (last > h->host_step) DQNB_FAIL("results of update %llu requested but only %llu were enqueued", last, h->host_step);
+  if (h->host_step - (unsigned long long)first_step >= (unsigned long long)h->max_slots) DQNB_FAIL("results of update %lld are no longer kept (%d slots)", (long long)first_step, h->max_slots);
+  DQNB_CUDA(cudaSetDevice(h->cfg.device));
+  unsigned spins = 0;
+  while (*h->h_done < last) {
+    if ((++spins & 0x3ff) == 0) {
+      const cudaError_t q = cudaStreamQuery(h->stream);
+      if (q == cudaSuccess) break;                         // stream drained: the counter is final
+      if (q != cudaErrorNotReady) DQNB_CUDA(q);
+    }
+  }
+  if (*h->h_done < last) DQNB_FAIL("update %llu did not complete (device reports %llu)", last, (unsigned long long)*h->h_done);
+  for (int i = 0; i < n; ++i) {
+    const int slot = (int)(((unsigned long long)first_step - 1 + i) % (unsigned long long)h->max_slots);
     if (critic_loss) critic_loss[i] = h->h_results[2 * slot];
     if (avg_q) avg_q[i] = h->h_results[2 * slot + 1];
   }
@@ -1389,6 +1520,7 @@ int dqnb_benchmark_gemms(dqnb_handle h, int32_t reps, float *ms_per_update, int3
 int dqnb_peek_sample_indices(dqnb_handle h, int32_t *idx) {
   if (!h || !idx) DQNB_FAIL("bad argument");
   DQNB_CUDA(cudaSetDevice(h->cfg.device));
+  if (order_compute_after_copies(h)) return -1;
   sample_kernel<<<(h->B + 255) / 256, 256, 0, h->stream>>>(h->st, h->cfg.seed, h->B, h->idx);
   DQNB_CUDA(cudaGetLastError());
   DQNB_CUDA(cudaMemcpyAsync(idx, h->idx, sizeof(int32_t) * h->B, cudaMemcpyDeviceToHost, h->stream));
@@ -1650,7 +1782,7 @@ int dqnb_gemm_test(int device, int gemm_mode, int a_mn, int b_mn, int M, int N, 
     if (r == 1) DQNB_CUDA(cudaEventRecord(e0, 0));
     p.dbg_clk = dclk + kTraceSlots * r;            // per-launch timeline slot
     if (gemm_mode == DQNB_GEMM_TCGEN05_3XTF32)
-      DQNB_CUDA(launch_k(tc_kernel_for(a_mn, b_mn, p.bn), op.grid, dim3(TC_THREADS), (size_t)tc_smem_for(p.bn), (cudaStream_t)0, op.gemm));
+      DQNB_CUDA(launch_k(tc_kernel_for(a_mn, b_mn, p.bn), op.grid, dim3(TC_THREADS), (size_t)tc_smem_for(p.bn, p.stages), (cudaStream_t)0, op.gemm));
     else gemm_simt_kernel<<<op.grid, 256>>>(op.gemm.p);
   }
   DQNB_CUDA(cudaEventRecord(e1, 0));

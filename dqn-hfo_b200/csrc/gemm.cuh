@@ -42,6 +42,8 @@ struct GemmParams {
   uint32_t *relu_bits_out; const uint32_t *relu_bits_in; int ldbits;
   int apply_lrelu;                            // EPI_FWD: 0 for linear layers
   int bn;                                     // N tile of the tcgen05 kernel: 64 or 128
+  int stages;                                 // depth of the TMA->MMA smem ring (2..4).  BN=64 with 2 stages is 98 KB
+                                              // per CTA: two CTAs share an SM, one's epilogue under the other's mainloop
   int cluster_k;                              // 1: launched as 2-CTA clusters along z; the CTAs split K and the
                                               //    leader adds its peer's partial tile over DSMEM before the epilogue
   int dbg;                                    // perf experiments (gemm_test only): bit0 skip MMA, bit1 skip TMA
@@ -174,8 +176,9 @@ struct TcCfg {
   static constexpr int A_STAGE_BYTES = 2 * A_PLANE_BYTES;      // hi + lo
   static constexpr int B_STAGE_BYTES = 2 * B_PLANE_BYTES;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;   // 48 / 64 KB
-  static constexpr int STAGES = (TC_SMEM_MAX - 2048) / STAGE_BYTES > 4 ? 4 : (TC_SMEM_MAX - 2048) / STAGE_BYTES;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 512 /*bias tile*/;
+  static constexpr int MAX_STAGES = (TC_SMEM_MAX - 2048) / STAGE_BYTES > 4 ? 4 : (TC_SMEM_MAX - 2048) / STAGE_BYTES;
+  static constexpr int MIN_STAGES = 2;          // also holds the epilogue's staging boxes (4 warps x BN/32 x 8 KB)
+  static constexpr int smem_bytes(int stages) { return stages * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 512 /*bias tile*/; }
   static constexpr int TMEM_COLS = 2 * BN_;                    // two fp32 accumulators of BN columns
 };
 constexpr int MN_GROUP_BYTES = 2 * 32 * BK * 4;       // MN-major: one 32-wide group, hi plane then lo plane
@@ -320,9 +323,9 @@ __device__ __forceinline__ float4 ld_dsmem_f4(uint32_t local_saddr, uint32_t ran
 template <int A_MN, int B_MN, int BN_>
 __device__ __forceinline__ void gemm_tc_body(const GemmArgs &args, const int n_tile, const int m_tile, const int split) {
   using Cfg = TcCfg<BN_>;
-  constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   const GemmParams &p = args.p;
+  const int STAGES = p.stages;
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;          // swizzle atoms need 1024 B alignment
   uint8_t *base_ptr = smem_raw + (base - raw);
@@ -368,9 +371,9 @@ __device__ __forceinline__ void gemm_tc_body(const GemmArgs &args, const int n_t
 
   if (warp == 0) {
     // ---------------- TMA producer ----------------
+    int s = 0;
+    uint32_t ph = 0;
     for (int it = 0; it < iters; ++it) {
-      const int s = it % STAGES;
-      const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
       const uint32_t full = bars + 8 * s, empty = bars + 8 * (STAGES + s);
       mbar_wait(empty, ph ^ 1u);
       if (elect_one()) {
@@ -397,15 +400,16 @@ __device__ __forceinline__ void gemm_tc_body(const GemmArgs &args, const int n_t
         }
       }
       __syncwarp();
+      if (++s == STAGES) { s = 0; ph ^= 1u; }
     }
   } else if (warp == 1) {
     // ---------------- MMA issuer ----------------
     constexpr uint32_t idesc = umma_idesc_tf32(A_MN, B_MN, BN_);
     constexpr uint32_t a_lo_off = A_MN ? 4096u : (uint32_t)Cfg::A_PLANE_BYTES;
     constexpr uint32_t b_lo_off = B_MN ? 4096u : (uint32_t)Cfg::B_PLANE_BYTES;
+    int s = 0;
+    uint32_t ph = 0;
     for (int it = 0; it < iters; ++it) {
-      const int s = it % STAGES;
-      const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
       const uint32_t full = bars + 8 * s, empty = bars + 8 * (STAGES + s);
       mbar_wait(full, ph);
       tc_fence_after();
@@ -431,6 +435,7 @@ __device__ __forceinline__ void gemm_tc_body(const GemmArgs &args, const int n_t
         tc_commit(empty);                  // frees the smem stage when these MMAs retire
       }
       __syncwarp();
+      if (++s == STAGES) { s = 0; ph ^= 1u; }
     }
     if (elect_one()) {
       tc_commit(tfull);                    // accumulators complete -> epilogue
@@ -451,8 +456,8 @@ __device__ __forceinline__ void gemm_tc_body(const GemmArgs &args, const int n_t
     constexpr int NCH = BN_ / 32;            // 32-column chunks of the tile
     constexpr int MYCH = NCH / 2;            // ... handled by this warp: chunks half, half + 2, ..
     static_assert(BN_ == 64 || BN_ == 128, "epilogue mapping assumes BN of 64 or 128");
-    static_assert(BM * LDS * 4 <= STAGES * Cfg::STAGE_BYTES, "peer partial tile must fit in the stage ring");
-    static_assert(4 * NCH * 2 * 4096 <= STAGES * Cfg::STAGE_BYTES, "staging boxes must fit in the stage ring");
+    static_assert(BM * LDS * 4 <= Cfg::MIN_STAGES * Cfg::STAGE_BYTES, "peer partial tile must fit in the stage ring");
+    static_assert(4 * NCH * 2 * 4096 <= Cfg::MIN_STAGES * Cfg::STAGE_BYTES, "staging boxes must fit in the stage ring");
     const int q = warp & 3;                  // TMEM lane quarter this warp may read
     const int half = warp >> 2;
     float *s_bias = reinterpret_cast<float *>(base_ptr + STAGES * Cfg::STAGE_BYTES + 256);
@@ -643,18 +648,23 @@ inline TcKernel tc_kernel_for(int a_mn, int b_mn, int bn) {
   if (a_mn && !b_mn) return gemm_tc_kernel<1, 0, 64>;
   return gemm_tc_kernel<1, 1, 64>;
 }
-inline int tc_smem_for(int bn) { return bn == 128 ? TcCfg<128>::SMEM_BYTES : TcCfg<64>::SMEM_BYTES; }
+inline int tc_max_stages(int bn) { return bn == 128 ? TcCfg<128>::MAX_STAGES : TcCfg<64>::MAX_STAGES; }
+inline int tc_smem_for(int bn, int stages) { return bn == 128 ? TcCfg<128>::smem_bytes(stages) : TcCfg<64>::smem_bytes(stages); }
+inline cudaError_t tc_prepare(const void *fn, int bn) {
+  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_for(bn, tc_max_stages(bn)));
+  if (e != cudaSuccess) return e;
+  // two 98 KB CTAs only share an SM if the carve-out leaves room for both
+  return cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
 inline cudaError_t tc_prepare_all() {
   {
-    cudaError_t e = cudaFuncSetAttribute((const void *)gemm_tc_grouped_kernel<1, 1, 64>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_for(64));
+    cudaError_t e = tc_prepare((const void *)gemm_tc_grouped_kernel<1, 1, 64>, 64);
     if (e != cudaSuccess) return e;
   }
   for (int bn : {64, 128})
     for (int a = 0; a < 2; ++a)
       for (int b = 0; b < 2; ++b) {
-        cudaError_t e = cudaFuncSetAttribute((const void *)tc_kernel_for(a, b, bn),
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_for(bn));
+        cudaError_t e = tc_prepare((const void *)tc_kernel_for(a, b, bn), bn);
         if (e != cudaSuccess) return e;
       }
   return cudaSuccess;

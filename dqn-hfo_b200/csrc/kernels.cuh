@@ -564,6 +564,7 @@ struct AdamArgs {
   // set on the last optimiser launch of an update: the block that finishes last publishes
   // (critic_loss, avg_q) and advances the iteration / sampler counters (formerly finalize_kernel)
   int finalize; unsigned int *ticket; const float *g_critic_tail, *g_actor_tail; float *results; int max_slots;
+  unsigned long long *done;         // mapped pinned word: number of finished updates (dqnb_results polls it)
 };
 __device__ __forceinline__ void adam_finalize(const AdamArgs &a) {
   __threadfence();
@@ -579,6 +580,10 @@ __device__ __forceinline__ void adam_finalize(const AdamArgs &a) {
   st->critic_iter += 1;                             // Solver::Step ++iter_ (dqn.cpp:904)
   st->actor_iter += 1;                              // set_iter(iter+1)     (dqn.cpp:965)
   st->step += 1;
+  if (a.done) {
+    __threadfence_system();                         // results first, then the counter the host spins on
+    *reinterpret_cast<volatile unsigned long long *>(a.done) = st->step;
+  }
 }
 __global__ void __launch_bounds__(256) adam_kernel(const AdamArgs a) {
   DQNB_PDL_PROLOGUE();

@@ -114,6 +114,15 @@ int dqnb_get_transitions(dqnb_handle h, int32_t first, int32_t n, float *s, floa
  * (counter-based Philox4x32-10 keyed by seed and update number; replaces
  * SampleTransitionsFromMemory dqn.cpp:501-509).  critic_loss / avg_q: [n_updates] or NULL. */
 int dqnb_update(dqnb_handle h, int32_t n_updates, float *critic_loss, float *avg_q);
+/* The same updates without waiting for them: the call returns once they are enqueued; *last_step is the
+ * 1-based sequence number of the last one.  dqnb_add_transitions stays legal while updates are in flight:
+ * appends travel on a copy stream, ordered after the last enqueued minibatch gather and before the next
+ * one, so every update samples exactly the memory the reference's sequential Update() (dqn.cpp:799-826)
+ * would have seen. */
+int dqnb_update_async(dqnb_handle h, int32_t n_updates, int64_t *last_step);
+/* (critic_loss, avg_q) of updates [first_step, first_step + n): blocks (spinning on a host-mapped counter
+ * the device publishes, no stream sync) until the last of them has finished.  The last 4096 updates are kept. */
+int dqnb_results(dqnb_handle h, int64_t first_step, int32_t n, float *critic_loss, float *avg_q);
 /* One UpdateActorCritic on caller-chosen deque indices idx[batch] (parity hook: the reference's
  * std::uniform_int_distribution stream is libstdc++-defined, so tests inject indices). */
 int dqnb_update_with_indices(dqnb_handle h, const int32_t *idx, float *critic_loss, float *avg_q);
