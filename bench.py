@@ -360,6 +360,8 @@ def main():
                 "algorithmic_flop_per_step": fpt * B,
                 "note": "3xTF32 issues 6 bf16-equivalent MMA passes per algorithmic product: ceiling = peak/6",
                 "frac_of_3xtf32_ceiling": ach / (bf16_sus / 6.0),
+                # the same FLOP over the whole update (the GEMMs of independent branches overlap inside the step)
+                "achieved_over_step": fpt * B / (ms_max / args.steps * 1e-3) / 1e12,
                 "share_of_step": gemm_ms / (ms_max / args.steps),
             }
         except Exception as e:  # keep the bench line even if the auxiliary measurement fails
@@ -391,7 +393,7 @@ def ncu_traffic_per_launch():
     the newest committed `ncu --set full` summary (profiles/*_ncu_gemm_full.txt).  None if no capture."""
     import glob
     import re
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_gemm_full.txt")), key=os.path.getmtime)
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_gemm_full.txt")), key=os.path.basename)   # r01 < r01b < r01d < r02 ..
     if not files:
         return None, None
     unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}

@@ -360,13 +360,17 @@ struct Tuning {
   int dw0_main;     // 1: the last weight-gradient GEMM (layer 0) follows the dX chain on the main stream
   int colsum_side;  // 1: bias column sums on side stream 1 beside that GEMM
   int dw_streams;   // 1: every weight-gradient GEMM on its own side stream, per-layer bias column sums on stream 2
+  int cluster_b;    // 1: cluster split-K also for the target chains, which share the machine with the side chains
+  int pdl_early;    // GEMM kernels: 1 = launch_dependents right after the wait, 0 = after the last MMA issue
   int bn_fwd, bn_fwd_side, bn_dx, bn_dw;   // N tile (64 / 128) per GEMM class
   int st_fwd, st_fwd_side, st_dx, st_dw;   // smem ring depth per GEMM class (0 = deepest that fits)
   Tuning() {
-    sched = env_int("DQNB_SCHED", 0);
+    sched = env_int("DQNB_SCHED", 1);
     dw0_main = env_int("DQNB_DW0_MAIN", 0);
     colsum_side = env_int("DQNB_COLSUM_SIDE", 0);
     dw_streams = env_int("DQNB_DW_STREAMS", 1);
+    cluster_b = env_int("DQNB_CLUSTER_B", 0);
+    pdl_early = env_int("DQNB_PDL_EARLY", 0);
     bn_fwd = env_int("DQNB_BN_FWD", 64);
     bn_fwd_side = env_int("DQNB_BN_FWD_SIDE", 64);
     bn_dx = env_int("DQNB_BN_DX", 64);
@@ -400,6 +404,7 @@ static int finish_gemm(const dqnb_config &cfg, Op *op) {
     const int a_rows = p.a_mn ? p.K : p.M, b_rows = p.b_mn ? p.K : p.N;
     if (p.bn != 64 && p.bn != 128) p.bn = 64;
     if (p.stages < 2 || p.stages > tc_max_stages(p.bn)) p.stages = tc_max_stages(p.bn);
+    p.pdl_early = tuning().pdl_early;
     if (p.epi == EPI_DX && !p.relu_bits_in) DQNB_FAIL("EPI_DX needs the sign bits of the saved activation");
     // Forward / dX GEMMs with a long contraction but few output tiles: split K over a 2-CTA cluster
     // (DSMEM reduction in the epilogue) so that the dependent chain sees half the mainloop latency.
@@ -608,13 +613,13 @@ static int run_ops(dqnb_handle_s *h, const std::vector<Op> &ops, cudaStream_t s,
 // building the op lists
 // ---------------------------------------------------------------------------------------------
 static int build_forward(dqnb_handle_s *h, const NetGeom &g, const float *P, const SplitMat &X,
-                         SplitMat *acts, std::vector<Op> &ops, bool critical_chain = true) {
+                         SplitMat *acts, std::vector<Op> &ops, bool critical_chain = true, bool allow_cluster = true) {
   const SplitMat *in = &X;
   for (int l = 0; l < g.n_hidden; ++l) {
     Op op;
     if (op_fwd(h->cfg, g, l, P, *in, acts[l], &op, critical_chain ? tuning().bn_fwd : tuning().bn_fwd_side,
                critical_chain ? tuning().st_fwd : tuning().st_fwd_side)) return -1;
-    if (!critical_chain && op.gemm.p.cluster_k) {
+    if ((!critical_chain || !allow_cluster) && op.gemm.p.cluster_k) {
       // side-branch passes run beside the critical chain: they should not grab twice the SMs for a
       // latency that nobody waits on, so they keep one CTA per tile
       op.gemm.p.cluster_k = 0; op.gemm.p.splits = 1; op.grid.z = 1;
@@ -636,7 +641,7 @@ static Op make_colsum(dqnb_handle_s *h, const NetGeom &g, int l0, int l1) {
   for (int l = l0; l < l1; ++l) {
     const int i = l - l0;
     a.dZ[i] = h->dZ[l].p; a.plane[i] = h->dZ[l].plane(); a.ld[i] = h->dZ[l].ld; a.Np[i] = g.L[l].Np;
-    a.b_off[i] = g.L[l].b_off; a.blk_begin[i] = blk; blk += (g.L[l].Np + 127) / 128;
+    a.b_off[i] = g.L[l].b_off; a.blk_begin[i] = blk; blk += (g.L[l].Np + kCsCols - 1) / kCsCols;
   }
   a.blk_begin[l1 - l0] = blk;
   a.gpart = h->Gpart[g.critic]; a.gpart_stride = h->gpart_stride[g.critic];
@@ -661,7 +666,6 @@ static int build_backward(dqnb_handle_s *h, const NetGeom &g, const float *P, co
     // the side streams pick up once dZ[top] exists
     Op f; f.kind = Op::FORK; f.mask = fork_mask; ops.push_back(f);
     if (head_bwd_w) { Op w = *head_bwd_w; w.branch = 2; ops.push_back(w); }
-    if (dws) { Op c = make_colsum(h, g, top, top + 1); c.branch = 2; ops.push_back(c); }
   }
   // Experiment kept behind DQNB_GROUPED_DW=1: the weight-gradient GEMMs of all layers as ONE grouped launch
   // after the dX chain.  Measured 2.75e6 vs 2.75-2.79e6 tr/s for the per-layer launches that overlap the
@@ -689,6 +693,9 @@ static int build_backward(dqnb_handle_s *h, const NetGeom &g, const float *P, co
         grp.group.tile_begin[i + 1] = grp.group.tile_begin[i] + (int)(op.grid.x * op.grid.y * op.grid.z);
       } else {
         ops.push_back(op);
+        // bias column sums of dZ[l] ride behind the weight gradient that waits for the same dZ; the last two
+        // (whose GEMMs form the tail of the pass) run beside their GEMMs on side stream 1, after the head gradient
+        if (dws && (l > 1 || l == top)) { Op c = make_colsum(h, g, l, l + 1); c.branch = 3 + l; ops.push_back(c); }
       }
       // segment table entries (internal flat order: W_l then b_l)
       SegTable &T = *segs;
@@ -700,7 +707,7 @@ static int build_backward(dqnb_handle_s *h, const NetGeom &g, const float *P, co
       if (op_dx(h->cfg, g, l, P, h->dZ[l], acts[l - 1], h->dZ[l - 1], &op)) return -1;
       if (want_dw) op.rec_ev = l - 1;                           // dZ[l-1] ready
       ops.push_back(op);
-      if (dws) { Op c = make_colsum(h, g, l - 1, l); c.branch = 2; c.wait_ev = l - 1; ops.push_back(c); }
+      if (dws && l <= 2) { Op c = make_colsum(h, g, l - 1, l); c.branch = 2; c.wait_ev = l - 1; ops.push_back(c); }
     }
   }
   if (grouped) {
@@ -851,13 +858,13 @@ static int build_update_ops(dqnb_handle_s *h) {
   };
   if (sched != 1 && push_actor_chain(side2, -1)) return -1;   // same side stream: at most two chains compete
   op.branch = 0;
-  if (build_forward(h, gA, PAT, h->Xsn, h->actAT, ops)) return -1;
+  if (build_forward(h, gA, PAT, h->Xsn, h->actAT, ops, true, tuning().cluster_b != 0)) return -1;
   op_head_fwd(gA, PAT, h->actAT[topA], h->B, h->a16_t, &h->Xct, h->S, &op);
   if (sched == 1) op.rec_ev = kEvActorStart;
   ops.push_back(op);
   op.rec_ev = -1;
   if (sched == 1 && push_actor_chain(2, kEvActorStart)) return -1;
-  if (build_forward(h, gC, PCT, h->Xct, h->actCT, ops)) return -1;
+  if (build_forward(h, gC, PCT, h->Xct, h->actCT, ops, true, tuning().cluster_b != 0)) return -1;
   push_critic_head(h, QMODE_TARGET, PCT, h->actCT[topC], h->q_next, ops);   // dqn.cpp:892-900
   op.kind = Op::JOIN; op.mask = fork_mask; ops.push_back(op);
   // rest of critic_solver_->Step(1): loss, backward, clip, Adam (+ soft update of the target critic)

@@ -46,6 +46,10 @@ struct GemmParams {
                                               // per CTA: two CTAs share an SM, one's epilogue under the other's mainloop
   int cluster_k;                              // 1: launched as 2-CTA clusters along z; the CTAs split K and the
                                               //    leader adds its peer's partial tile over DSMEM before the epilogue
+  int pdl_early;                              // 1: release the dependent grid right after griddepcontrol.wait (its CTAs
+                                              //    then sit on SMs - 197 KB of smem each - for this kernel's whole
+                                              //    duration); 0: when the last MMA has been issued, so they only overlap
+                                              //    the accumulator drain + epilogue (measured: profiles/r01c_*)
   int dbg;                                    // perf experiments (gemm_test only): bit0 skip MMA, bit1 skip TMA
   long long *dbg_clk;                         // optional: MMA-thread clock64 stamps {start, issued, complete}
 };
@@ -365,7 +369,7 @@ __device__ __forceinline__ void gemm_tc_body(const GemmArgs &args, const int n_t
   // Everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps the tail of the
   // previous kernel; from here on we read what it wrote.
   pdl_wait();
-  pdl_launch_dependents();
+  if (p.pdl_early) pdl_launch_dependents();
   if (threadIdx.x == 0) DQNB_STAMP(2);
   if (p.dbg_clk && threadIdx.x == 0) atomicMax(p.dbg_clk + 1, (long long)gtime_ns());   // latest CTA to pass the wait
 
@@ -441,6 +445,7 @@ __device__ __forceinline__ void gemm_tc_body(const GemmArgs &args, const int n_t
       tc_commit(tfull);                    // accumulators complete -> epilogue
     }
     __syncwarp();
+    if (!p.pdl_early) pdl_launch_dependents();   // every MMA is issued: the next kernel's prologue overlaps our tail
   }
   {
     // ---------------- epilogue: TMEM -> registers -> swizzled smem -> TMA store ----------------

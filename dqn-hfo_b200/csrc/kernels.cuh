@@ -453,29 +453,33 @@ __global__ void __launch_bounds__(256) head_bwd_w_kernel(const HeadBwdWArgs a) {
 }
 
 // Bias gradients of the tower layers: db_l[c] = sum_n dZ_l[n][c] (Caffe: gemv(dY^T, ones)).
+// grid (column blocks of 32 over all layers, kGradSplits row slices); 1024 threads = 32 row sub-groups x 32
+// columns: every warp reads 128 contiguous bytes of one row, and a thread adds rows_pad / (8 * 32) rows, so
+// the kernel is many short independent chains (it sits beside the tail of the backward pass).
+constexpr int kCsCols = 32, kCsSub = 32;
 struct ColsumArgs {
   long long *trace;              // DQNB_TRACE timeline slot (nullable)
   int n_layers, rows_pad;
   const float *dZ[8]; long long plane[8]; int ld[8]; int Np[8]; long long b_off[8];
-  int blk_begin[9];            // prefix sums of Np/128 column blocks
+  int blk_begin[9];            // prefix sums of Np/32 column blocks
   float *gpart; long long gpart_stride;
 };
 __global__ void __launch_bounds__(1024) colsum_kernel(const ColsumArgs a) {
   DQNB_PDL_PROLOGUE();
   trace_begin(a.trace);
-  __shared__ float red[kRedSub][128];
+  __shared__ float red[kCsSub][kCsCols + 1];
   int l = 0;
   while (l + 1 < a.n_layers && (int)blockIdx.x >= a.blk_begin[l + 1]) ++l;
-  const int col = threadIdx.x & 127, sub = threadIdx.x >> 7, split = blockIdx.y;
-  const int c = ((int)blockIdx.x - a.blk_begin[l]) * 128 + col;
+  const int col = threadIdx.x & (kCsCols - 1), sub = threadIdx.x / kCsCols, split = blockIdx.y;
+  const int c = ((int)blockIdx.x - a.blk_begin[l]) * kCsCols + col;
   const int per = a.rows_pad / kGradSplits;
   const int r0 = split * per, r1 = r0 + per;
   const float *zh = a.dZ[l], *zl = a.dZ[l] + a.plane[l];
   const int ld = a.ld[l];
   float acc = 0.f;
   if (c < a.Np[l]) {
-#pragma unroll 8
-    for (int n = r0 + sub; n < r1; n += kRedSub) {
+#pragma unroll 4
+    for (int n = r0 + sub; n < r1; n += kCsSub) {
       const long long o = (long long)n * ld + c;
       acc += zh[o] + zl[o];
     }
@@ -485,7 +489,7 @@ __global__ void __launch_bounds__(1024) colsum_kernel(const ColsumArgs a) {
   if (sub == 0 && c < a.Np[l]) {
     float s = 0.f;
 #pragma unroll
-    for (int t = 0; t < kRedSub; ++t) s += red[t][col];
+    for (int t = 0; t < kCsSub; ++t) s += red[t][col];
     a.gpart[(long long)split * a.gpart_stride + a.b_off[l] + c] = s;
   }
   trace_end(a.trace);

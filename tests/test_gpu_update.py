@@ -18,6 +18,12 @@ SHAPES = [
     pytest.param(59, 32, (1024, 512, 256, 128), "warm", id="cfg1-S59-B32-warm"),
     pytest.param(58, 256, (256, 128, 64, 64), "warm", id="S58-B256-small"),
     pytest.param(77, 100, (192, 96, 48, 32), "warm", id="S77-B100-ragged"),
+    # tower depths other than the reference's four (dqn.cpp:425 is a literal, prototxt-defined nets are not):
+    # the per-layer gradient streams / column-sum placement of the op list depend on the depth
+    pytest.param(58, 64, (128,), "warm", id="depth1"),
+    pytest.param(58, 64, (128, 64), "warm", id="depth2"),
+    pytest.param(58, 64, (128, 96, 64), "warm", id="depth3"),
+    pytest.param(58, 64, (128, 96, 64, 64, 32, 32), "warm", id="depth6"),
 ]
 
 
