@@ -362,6 +362,8 @@ struct Tuning {
   int dw_streams;   // 1: every weight-gradient GEMM on its own side stream, per-layer bias column sums on stream 2
   int cluster_b;    // 1: cluster split-K also for the target chains, which share the machine with the side chains
   int pdl_early;    // GEMM kernels: 1 = launch_dependents right after the wait, 0 = after the last MMA issue
+  int bn_big;       // 128: dX / dW GEMMs that fill the machine with 128x64 tiles anyway use 128x128 tiles (half the CTAs,
+                    //      1.6x the tensor rate per CTA), so the two big GEMMs of a backward pass run side by side
   int bn_fwd, bn_fwd_side, bn_dx, bn_dw;   // N tile (64 / 128) per GEMM class
   int st_fwd, st_fwd_side, st_dx, st_dw;   // smem ring depth per GEMM class (0 = deepest that fits)
   Tuning() {
@@ -371,6 +373,7 @@ struct Tuning {
     dw_streams = env_int("DQNB_DW_STREAMS", 1);
     cluster_b = env_int("DQNB_CLUSTER_B", 0);
     pdl_early = env_int("DQNB_PDL_EARLY", 0);
+    bn_big = env_int("DQNB_BN_BIG", 64);
     bn_fwd = env_int("DQNB_BN_FWD", 64);
     bn_fwd_side = env_int("DQNB_BN_FWD_SIDE", 64);
     bn_dx = env_int("DQNB_BN_DX", 64);
@@ -454,6 +457,7 @@ static int op_dx(const dqnb_config &cfg, const NetGeom &g, int l, const float *P
   memset(&p, 0, sizeof(p));
   p.bn = (tuning().bn_dx == 128 && L.Kp % 128 == 0) ? 128 : 64;
   p.stages = tuning().st_dx;
+  if (tuning().bn_big == 128 && L.Kp % 128 == 0 && ((dZl.rows + BM - 1) / BM) * (L.Kp / 64) >= 128) { p.bn = 128; p.stages = 0; }
   p.M = dZl.rows; p.N = L.Kp; p.K = L.Np; p.a_mn = 0; p.b_mn = 1; p.splits = 1; p.epi = EPI_DX;
   p.A = dZl.p; p.a_plane = dZl.plane(); p.lda = dZl.ld;
   p.B = P + L.w_off; p.b_plane = g.flat; p.ldb = L.Kp;
@@ -487,6 +491,7 @@ static int op_dw(const dqnb_config &cfg, const NetGeom &g, int l, const SplitMat
   p.M = L.Np; p.N = L.Kp; p.K = dZl.rows; p.a_mn = 1; p.b_mn = 1; p.epi = EPI_PLAIN;
   p.bn = (tuning().bn_dw == 128 && L.Kp % 128 == 0) ? 128 : 64;
   p.stages = tuning().st_dw;
+  if (tuning().bn_big == 128 && L.Kp % 128 == 0 && ((L.Np + BM - 1) / BM) * (L.Kp / 64) >= 64) { p.bn = 128; p.stages = 0; }
   const int tiles = ((p.M + BM - 1) / BM) * ((p.N + p.bn - 1) / p.bn);
   p.splits = pick_splits(tiles, p.K / BK, kGradSplits);
   *splits_out = p.splits;
@@ -1775,6 +1780,7 @@ int dqnb_gemm_test(int device, int gemm_mode, int a_mn, int b_mn, int M, int N, 
   GemmParams &p = op.gemm.p;
   memset(&p, 0, sizeof(p));
   p.dbg = dbg & 3;
+  p.stages = (dbg >> 4) & 0xf;           // 0: deepest ring that fits
   p.bn = (dbg >> 8) ? (dbg >> 8) : 64;
   p.dbg_clk = dclk;
   p.M = M; p.N = N; p.K = K; p.a_mn = a_mn; p.b_mn = b_mn; p.splits = splits; p.epi = EPI_PLAIN;

@@ -39,6 +39,23 @@ def test_gemm_matches_float64(mode, a_mn, b_mn, M, N, K, splits):
     assert relerr(Cm, ref) < tol, (relerr(Cm, ref), ms)
 
 
+@pytest.mark.parametrize("bn,stages", [(128, 0), (128, 2), (64, 2), (64, 3)])
+@pytest.mark.parametrize("a_mn,b_mn,M,N,K,splits", [(0, 0, 1024, 512, 1024, 1), (0, 1, 1024, 1024, 512, 1), (1, 1, 512, 1024, 1024, 2),
+                                                    (1, 1, 64, 128, 256, 4), (0, 0, 256, 192, 96, 1)])
+def test_gemm_tile_and_ring_variants(bn, stages, a_mn, b_mn, M, N, K, splits):
+    """128x128 tiles and shallower TMA->MMA rings (two CTAs per SM) of the tcgen05 kernel; N=192 leaves the last
+    128-wide tile half outside the matrix (TMA clips loads and stores)."""
+    P = pkg()
+    rng = np.random.default_rng(7 * M + N + K + bn + stages)
+    A = rng.normal(0, 1, (M, K)).astype(np.float32)
+    B = rng.normal(0, 1, (N, K)).astype(np.float32)
+    ref = A.astype(np.float64) @ B.astype(np.float64).T
+    Ain = np.ascontiguousarray(A.T) if a_mn else A
+    Bin = np.ascontiguousarray(B.T) if b_mn else B
+    Cm, ms = P.gemm_test(0 | (stages << 12) | (bn << 16), a_mn, b_mn, M, N, K, splits, Ain, Bin)
+    assert relerr(Cm, ref) < 2e-5, (relerr(Cm, ref), ms)
+
+
 def test_gemm_exact_on_small_integers():
     """Integer-valued operands are exact in TF32, so any layout/descriptor bug shows up as a
     bit-level mismatch rather than a tolerance question."""
