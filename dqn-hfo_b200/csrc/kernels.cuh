@@ -359,7 +359,13 @@ __global__ void __launch_bounds__(256) actor_head_bwd_kernel(const ActorHeadBwdA
   if (n >= a.rows_pad) return;
   float diff = 0.f;
   if (n < a.B && lane < kActorOut) {
-    for (int sp = 0; sp < a.din_splits; ++sp) diff += a.d_in[sp * a.din_stride + (long long)n * a.ldin + a.S + lane];
+    float part[kGradSplits];
+#pragma unroll
+    for (int sp = 0; sp < kGradSplits; ++sp)       // all partial planes in flight, then summed in plane order
+      if (sp < a.din_splits) part[sp] = a.d_in[sp * a.din_stride + (long long)n * a.ldin + a.S + lane];
+#pragma unroll
+    for (int sp = 0; sp < kGradSplits; ++sp)
+      if (sp < a.din_splits) diff += part[sp];
     a.tap_raw[n * kActorOut + lane] = diff;
     const float output = a.a16[(long long)n * 16 + lane];
     float mn, mx;
@@ -523,11 +529,16 @@ __global__ void __launch_bounds__(256) reduce_kernel(const ReduceArgs a) {
       int s = 0;
       while (s + 1 < a.segs.n && i >= a.segs.end[s]) ++s;
       const int ns = a.segs.nsplit[s];
-      g = *reinterpret_cast<const float4 *>(a.gpart + i);
-      for (int p = 1; p < ns; ++p) {
-        const float4 t = *reinterpret_cast<const float4 *>(a.gpart + (long long)p * a.gpart_stride + i);
-        g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
-      }
+      // every plane's load is issued before the first add (a load-add-load-add loop is one L2 round trip per
+      // plane); the summation order stays plane 0, 1, 2, ..
+      float4 t[kGradSplits];
+#pragma unroll
+      for (int p = 0; p < kGradSplits; ++p)
+        if (p < ns) t[p] = *reinterpret_cast<const float4 *>(a.gpart + (long long)p * a.gpart_stride + i);
+      g = t[0];
+#pragma unroll
+      for (int p = 1; p < kGradSplits; ++p)
+        if (p < ns) { g.x += t[p].x; g.y += t[p].y; g.z += t[p].z; g.w += t[p].w; }
       *reinterpret_cast<float4 *>(a.G + i) = g;
     } else {
       g = *reinterpret_cast<const float4 *>(a.G + i);
@@ -609,6 +620,9 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamArgs a) {
     }
     __syncthreads();
   }
+  // (Requesting the operands before the norm reduction was tried: 48 instead of 40 registers, so the 804 blocks
+  // of the critic no longer fit in one wave - 9.8 us instead of 7.7.  The kernel moves 52 B per parameter, mostly
+  // from HBM: it is bandwidth-bound as it stands.)
   const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i >= a.flat) {
     if (a.finalize) adam_finalize(a);
