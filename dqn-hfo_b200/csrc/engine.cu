@@ -255,8 +255,9 @@ struct dqnb_handle_s {
   int S, Sp, Kc, B, Bp, An /*act rows pad*/;
   NetGeom gA, gC;
   cudaStream_t stream = nullptr;
-  // side streams -> parallel branches of the captured graph.  0, 1: independent forward chains / head gradients;
-  // 2 + l: the weight-gradient GEMM of tower layer l (each starts as soon as its dZ exists)
+  // side streams -> parallel branches of the captured graph (Op::branch b runs on side[b - 1]).  Branches 1, 2:
+  // independent forward chains / head gradients / column sums; 3 + l: the weight-gradient GEMM of tower layer l
+  // (each starts as soon as its dZ exists)
   cudaStream_t side[kMaxSide] = {};
   cudaEvent_t ev_fork = nullptr, ev_join[kMaxSide] = {};
   cudaEvent_t evs[8] = {};                            // cross-branch edges inside one update
@@ -656,7 +657,7 @@ static Op make_colsum(dqnb_handle_s *h, const NetGeom &g, int l0, int l1) {
 
 // tower backward from dZ[top] (already masked by the head backward).  The dX chain is the critical
 // path and stays on the main stream.  With want_dw every weight-gradient GEMM runs on a side stream of its
-// own (side 2 + l) and the head gradient + per-layer bias column sums on side 1, each gated by an event on
+// own (branch 3 + l) and the head gradient + the last bias column sums on branch 2, each gated by an event on
 // the dZ it consumes, so a gradient starts the moment its dZ exists; all JOIN back before the reduction.
 static int build_backward(dqnb_handle_s *h, const NetGeom &g, const float *P, const SplitMat &X,
                           SplitMat *acts, bool want_dw, SegTable *segs, const Op *head_bwd_w,
@@ -699,7 +700,7 @@ static int build_backward(dqnb_handle_s *h, const NetGeom &g, const float *P, co
       } else {
         ops.push_back(op);
         // bias column sums of dZ[l] ride behind the weight gradient that waits for the same dZ; the last two
-        // (whose GEMMs form the tail of the pass) run beside their GEMMs on side stream 1, after the head gradient
+        // (whose GEMMs form the tail of the pass) run beside their GEMMs on branch 2, after the head gradient
         if (dws && (l > 1 || l == top)) { Op c = make_colsum(h, g, l, l + 1); c.branch = 3 + l; ops.push_back(c); }
       }
       // segment table entries (internal flat order: W_l then b_l)
@@ -835,15 +836,16 @@ static int build_update_ops(dqnb_handle_s *h) {
     ops.push_back(op);
   }
   op.variant = 0;
-  // Three independent forward chains run side by side (separate streams -> parallel graph branches):
+  // Independent forward chains on separate streams (-> parallel graph branches):
   //   main  : dqn.cpp:889-891 CriticForwardThroughActor(critic_target, actor_target, s') + TD target
   //   side 1: forward half of critic_solver_->Step(1) on (s, a, p)            (dqn.cpp:904)
   //   side 2: actor forward on s with the pre-update actor                    (dqn.cpp:910-911)
-  // sched 1: only two chains compete at any time: (target actor || critic), then (target critic || actor).  The
-  // actor chain waits for the target actor's head (event 7) and is joined with the critic's gradient branch,
-  // long before its consumer (the critic forward on (s, a_pi)) runs.
+  // sched 1 (default): only two chains compete for the SMs at any time: (target actor || critic), then
+  // (target critic || actor).  The actor chain waits for the target actor's head (event 7) and is joined with the
+  // critic's gradient branches, long before its consumer (the critic forward on (s, a_pi)) runs.
+  // sched 0: all three from the start (the previous default; DQNB_SIDE_SERIAL=1 puts both side chains on one stream).
   const int sched = tuning().sched;
-  const int side2 = getenv("DQNB_SIDE_SERIAL") ? 1 : 2;   // measured: three concurrent chains beat two (2.78e6 vs 2.73e6 tr/s)
+  const int side2 = getenv("DQNB_SIDE_SERIAL") ? 1 : 2;
   const int fork_mask = sched == 1 ? 1 : (side2 == 2 ? 3 : 1);
   constexpr int kEvActorStart = 7;
   op.kind = Op::FORK; op.mask = fork_mask; ops.push_back(op);
@@ -910,7 +912,7 @@ static int build_update_ops(dqnb_handle_s *h) {
   return 0;
 }
 
-// DQNB_TRACE=1: every op of the update sequence gets an 8-slot timeline record (kernels.cuh trace_begin/end)
+// DQNB_TRACE=1: every op of the update sequence gets a kTraceSlots-slot timeline record (kernels.cuh trace_begin/end)
 static void attach_trace(dqnb_handle_s *h) {
   if (!h->trace) return;
   for (int i = 0; i < (int)h->update_ops.size() && i < h->trace_ops; ++i) {
