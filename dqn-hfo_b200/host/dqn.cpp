@@ -42,6 +42,10 @@ DEFINE_int32(device, 0, "CUDA device ordinal");
 DEFINE_bool(host_sampling, false, "Draw minibatch indices on the host with std::mt19937 exactly like "
                                   "SampleTransitionsFromMemory (default: device Philox sampler)");
 DEFINE_double(init_std, 0.01, "Std of the gaussian weight filler (dqn.cpp:352)");
+DEFINE_bool(async_update, false, "Update() enqueues the update and books the loss of the PREVIOUS one (dqnb_update_async / "
+                                 "dqnb_results): episodes, AddTransitions and logging overlap the GPU work.  The sampled "
+                                 "memories, weights and iteration counts are those of the blocking loop; only the "
+                                 "smoothed-loss log lags by one update");
 
 #define DQNB_OK(call)                                                         \
   do {                                                                        \
@@ -318,13 +322,24 @@ std::vector<int> DQN::SampleTransitionsFromMemory(int n) {  // dqn.cpp:501-509
 
 std::pair<float, float> DQN::UpdateActorCritic() {
   float loss = 0.f, avg_q = 0.f;
+  if (FLAGS_async_update && !FLAGS_host_sampling) {
+    long long step = 0;
+    DQNB_OK(dqnb_update_async(h_, 1, (int64_t *)&step));
+    if (!iters_dirty_) { actor_iter_cache_ += 1; critic_iter_cache_ += 1; }   // Solver::Step ++iter_, set_iter(iter+1)
+    if (pending_step_ > 0) {                     // the update enqueued by the previous call has had a whole env step
+      DQNB_OK(dqnb_results(h_, pending_step_, 1, &loss, &avg_q));
+      CHECK(std::isfinite(loss)) << "Critic loss not finite!";   // dqn.cpp:906
+    }
+    pending_step_ = step;
+    return std::make_pair(loss, avg_q);
+  }
   if (FLAGS_host_sampling) {
     const std::vector<int> idx = SampleTransitionsFromMemory(batch_size_);
     DQNB_OK(dqnb_update_with_indices(h_, idx.data(), &loss, &avg_q));
   } else {
     DQNB_OK(dqnb_update(h_, 1, &loss, &avg_q));
   }
-  iters_dirty_ = true;
+  if (!iters_dirty_) { actor_iter_cache_ += 1; critic_iter_cache_ += 1; }   // no device read per update
   CHECK(std::isfinite(loss)) << "Critic loss not finite!";   // dqn.cpp:906
   return std::make_pair(loss, avg_q);
 }

@@ -112,6 +112,7 @@ class DQN {
   mutable int actor_iter_cache_, critic_iter_cache_;
   mutable bool iters_dirty_;
   std::pair<float, float> last_update_;
+  long long pending_step_ = 0;   // -async_update: sequence number of the update whose results are still to be read
 };
 
 caffe::NetParameter CreateActorNet(int state_size);    // dqn.cpp:418-429

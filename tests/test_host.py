@@ -69,6 +69,17 @@ def test_dqn_main_benchmark_train_snapshot_resume(tmp_path):
     assert any(s.endswith(".solverstate") and "_actor_iter_" in s for s in snaps), snaps
     assert any(s.endswith(".caffemodel") and "_critic_iter_" in s for s in snaps), snaps
     assert any(s.endswith(".replaymemory") for s in snaps), snaps
+    # -async_update: Update() enqueues and books the previous update's loss; the learner state must not change
+    prefix_a = str(tmp_path / "arun")
+    args_a = [a if not a.startswith("-save=") else f"-save={prefix_a}" for a in args] + ["-async_update"]
+    out_a = subprocess.run(args_a, capture_output=True, text=True, timeout=600)
+    assert out_a.returncode == 0, out_a.stderr[-3000:]
+    assert re.search(r"\[Agent0\] Critic Iteration \d+, loss = ", out_a.stderr)
+    for kind in ("actor", "critic"):
+        fa = sorted(glob.glob(prefix + f"_agent0_{kind}_iter_*.caffemodel"))
+        fb = sorted(glob.glob(prefix_a + f"_agent0_{kind}_iter_*.caffemodel"))
+        assert fa and [os.path.basename(f).replace("arun", "run") for f in fb] == [os.path.basename(f) for f in fa], (fa, fb)
+        assert open(fa[-1], "rb").read() == open(fb[-1], "rb").read(), kind    # same updates, bit for bit
     # resume: picks up the newest snapshot and continues past its iteration (dqn_main.cpp:213-220,:268-286)
     args2 = [a if not a.startswith("-max_iter") else "-max_iter=160" for a in args]
     out2 = subprocess.run(args2, capture_output=True, text=True, timeout=600)
