@@ -193,7 +193,14 @@ DQN::DQN(caffe::SolverParameter &actor_solver_param, caffe::SolverParameter &cri
   dqnb_config c;
   dqnb_default_config(&c);
   c.device = FLAGS_device; c.state_size = state_size; c.batch = batch_size_;
-  const std::vector<int> hidden = parse_hidden(FLAGS_hidden);
+  // the tower comes with the solver parameters (CreateActorNet / a user's .prototxt, dqn_main.cpp:232-246);
+  // both nets share one width list in this build
+  const std::vector<int> hidden = actor_solver_param.net_param_.hidden.empty() ? parse_hidden(FLAGS_hidden)
+                                                                                : actor_solver_param.net_param_.hidden;
+  if (!critic_solver_param.net_param_.hidden.empty())
+    CHECK(critic_solver_param.net_param_.hidden == hidden) << "actor and critic towers of different widths are not implemented";
+  if (actor_solver_param.net_param_.state_size > 0) CHECK_EQ(actor_solver_param.net_param_.state_size, state_size);
+  if (critic_solver_param.net_param_.state_size > 0) CHECK_EQ(critic_solver_param.net_param_.state_size, state_size);
   CHECK_LE((int)hidden.size(), DQNB_MAX_HIDDEN);
   c.n_hidden = (int)hidden.size();
   for (size_t i = 0; i < hidden.size(); ++i) c.hidden[i] = hidden[i];

@@ -34,6 +34,19 @@ constexpr auto kMinibatchSize = 32;        // dqn.hpp:19 (default of -batch_size
 constexpr auto kActionSize = 4;            // dqn.hpp:20
 constexpr auto kActionParamSize = 6;       // dqn.hpp:21
 
+// Layer / blob names of the two nets (dqn.hpp:38-51); they appear in the .prototxt files
+constexpr auto state_input_layer_name = "state_input_layer";
+constexpr auto action_input_layer_name = "action_input_layer";
+constexpr auto action_params_input_layer_name = "action_params_input_layer";
+constexpr auto target_input_layer_name = "target_input_layer";
+constexpr auto q_values_layer_name = "q_values_layer";
+constexpr auto states_blob_name = "states";
+constexpr auto actions_blob_name = "actions";
+constexpr auto action_params_blob_name = "action_params";
+constexpr auto targets_blob_name = "target";
+constexpr auto q_values_blob_name = "q_values";
+constexpr auto loss_blob_name = "loss";
+
 using ActorOutput = std::array<float, kActionSize + kActionParamSize>;
 using StateData = std::vector<float>;
 using StateDataSp = std::shared_ptr<StateData>;
@@ -117,6 +130,13 @@ class DQN {
 
 caffe::NetParameter CreateActorNet(int state_size);    // dqn.cpp:418-429
 caffe::NetParameter CreateCriticNet(int state_size);   // dqn.cpp:431-454
+// <prefix>_{actor,critic}.prototxt (dqn_main.cpp:232-246), protobuf text format: what WriteProtoToTextFile
+// emits for the nets above / a parser for that family of files (tower widths and state size are honoured,
+// anything the kernels do not implement aborts).  prototxt.cpp
+std::string NetPrototxt(const caffe::NetParameter &np, int batch_size = kMinibatchSize);
+void WriteNetPrototxt(const caffe::NetParameter &np, const std::string &filename, int batch_size = kMinibatchSize);
+void ParseNetPrototxtOrDie(const std::string &text, const std::string &origin, bool critic, caffe::NetParameter *np);
+void ReadNetPrototxtOrDie(const std::string &filename, bool critic, caffe::NetParameter *np);
 
 Action GetAction(const ActorOutput &actor_output);     // dqn.cpp:196-208
 std::vector<std::string> FilesMatchingRegexp(const std::string &regexp);   // dqn.cpp:559-580

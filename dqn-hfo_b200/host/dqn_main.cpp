@@ -11,6 +11,8 @@
 #include <limits>
 #include <tuple>
 
+#include <sys/stat.h>
+
 #include "dqn.hpp"
 #include "hfo_game.hpp"
 #include "shim/flags.hpp"
@@ -49,7 +51,7 @@ DEFINE_int32(defense_agents, 0, "Number of agents playing defense");
 DEFINE_int32(defense_npcs, 0, "Number of npcs playing defense");
 DEFINE_int32(frames_per_trial, 500, "Episode length cap of the in-process environment (--frames-per-trial upstream)");
 DEFINE_int32(benchmark_iters, 1000, "Updates timed by -benchmark (dqn.cpp:487 default)");
-namespace dqn { DECLARE_int32(seed); }
+namespace dqn { DECLARE_int32(seed); DECLARE_int32(batch_size); }
 using dqn::FLAGS_seed;
 
 double CalculateEpsilon(const int iter) {  // dqn_main.cpp:65-71
@@ -141,8 +143,23 @@ void KeepPlayingGames(int tid, std::string save_prefix, int port) {  // dqn_main
   actor_solver_param.set_momentum(FLAGS_momentum); critic_solver_param.set_momentum(FLAGS_momentum);
   actor_solver_param.set_momentum2(FLAGS_momentum2); critic_solver_param.set_momentum2(FLAGS_momentum2);
   actor_solver_param.set_clip_gradients(FLAGS_clip_grad); critic_solver_param.set_clip_gradients(FLAGS_clip_grad);
-  *actor_solver_param.mutable_net_param() = dqn::CreateActorNet(num_features);
-  *critic_solver_param.mutable_net_param() = dqn::CreateCriticNet(num_features);
+  // dqn_main.cpp:232-246: the nets are described by <prefix>_{actor,critic}.prototxt; an existing file wins
+  // (that is how a run's architecture is changed upstream), otherwise the default net is created and written
+  struct stat st;
+  const std::string actor_net_filename = save_prefix + "_actor.prototxt", critic_net_filename = save_prefix + "_critic.prototxt";
+  const bool net_files = !FLAGS_save.empty();   // -benchmark / -evaluate may run without a save prefix: no files then
+  if (net_files && stat(actor_net_filename.c_str(), &st) == 0 && S_ISREG(st.st_mode)) {
+    dqn::ReadNetPrototxtOrDie(actor_net_filename, false, actor_solver_param.mutable_net_param());
+  } else {
+    *actor_solver_param.mutable_net_param() = dqn::CreateActorNet(num_features);
+    if (net_files) dqn::WriteNetPrototxt(*actor_solver_param.mutable_net_param(), actor_net_filename, dqn::FLAGS_batch_size);
+  }
+  if (net_files && stat(critic_net_filename.c_str(), &st) == 0 && S_ISREG(st.st_mode)) {
+    dqn::ReadNetPrototxtOrDie(critic_net_filename, true, critic_solver_param.mutable_net_param());
+  } else {
+    *critic_solver_param.mutable_net_param() = dqn::CreateCriticNet(num_features);
+    if (net_files) dqn::WriteNetPrototxt(*critic_solver_param.mutable_net_param(), critic_net_filename, dqn::FLAGS_batch_size);
+  }
 
   dqn::DQN *dqn = new dqn::DQN(actor_solver_param, critic_solver_param, save_prefix, num_features, tid);
   if (!actor_snapshot.empty()) dqn->RestoreActorSolver(actor_snapshot);

@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <string>
 
 #include "dqn.hpp"
 #include "hfo_game.hpp"
@@ -40,6 +41,41 @@ int main() {
     o[0] = 0.7f; a = dqn::GetAction(o);
     EXPECT(a.action == hfo::DASH && a.arg1 == 10.f && a.arg2 == 20.f);
     EXPECT(dqn::PrintActorOutput(o).find("Dash(10.000000, 20.000000)=0.700000") == 0);
+  }
+  {  // <prefix>_{actor,critic}.prototxt (dqn_main.cpp:232-246): what we write is what we read ...
+    shim::set_flag("hidden", "1024,512,256,128");
+    for (int critic = 0; critic < 2; ++critic) {
+      const caffe::NetParameter np = critic ? dqn::CreateCriticNet(59) : dqn::CreateActorNet(59);
+      const std::string text = dqn::NetPrototxt(np, 32);
+      EXPECT(text.find("name: \"" + std::string(critic ? "Critic" : "Actor") + "\"") == 0);
+      EXPECT(text.find("force_backward: true") != std::string::npos);
+      EXPECT(text.find("height: 59") != std::string::npos);
+      EXPECT(text.find("name: \"ip4_relu_layer\"") != std::string::npos && text.find("negative_slope: 0.01") != std::string::npos);
+      EXPECT((text.find("name: \"q_values_layer\"") != std::string::npos) == (critic == 1));
+      EXPECT((text.find("name: \"actionpara_layer\"") != std::string::npos) == (critic == 0));
+      EXPECT((text.find("type: \"Concat\"") != std::string::npos) == (critic == 1));
+      caffe::NetParameter back;
+      dqn::ParseNetPrototxtOrDie(text, "roundtrip", critic != 0, &back);
+      EXPECT(back.hidden == np.hidden && back.state_size == 59 && back.critic == (critic != 0) && back.name() == np.name());
+    }
+    // ... and a hand-edited file of the same family (comments, other widths and depth, single-line messages,
+    // the `field: { }` spelling) gives the tower the user asked for
+    const char *edited =
+        "# a narrower actor\n"
+        "name: \"Actor\"  force_backward: true\n"
+        "layer { name: \"state_input_layer\" type: \"MemoryData\" top: \"states\" top: \"dummy1\"\n"
+        "        memory_data_param { batch_size: 32 channels: 1 height: 77 width: 1 } }\n"
+        "layer { name: \"silence\" type: \"Silence\" bottom: \"dummy1\" }\n"
+        "layer { name: \"ip1_layer\" type: \"InnerProduct\" bottom: \"states\" top: \"ip1\"\n"
+        "        inner_product_param: { num_output: 300 weight_filler { type: \"gaussian\" std: 0.01 } } }\n"
+        "layer { name: \"ip1_relu_layer\" type: \"ReLU\" bottom: \"ip1\" top: \"ip1\" relu_param { negative_slope: 0.01 } }\n"
+        "layer { name: \"ip2_layer\" type: \"InnerProduct\" bottom: \"ip1\" top: \"ip2\" inner_product_param { num_output: 200 } }\n"
+        "layer { name: \"ip2_relu_layer\" type: \"ReLU\" bottom: \"ip2\" top: \"ip2\" relu_param { negative_slope: 1e-2 } }\n"
+        "layer { name: \"action_layer\" type: \"InnerProduct\" bottom: \"ip2\" top: \"actions\" inner_product_param { num_output: 4 } }\n"
+        "layer { name: \"actionpara_layer\" type: \"InnerProduct\" bottom: \"ip2\" top: \"action_params\" inner_product_param { num_output: 6 } }\n";
+    caffe::NetParameter ed;
+    dqn::ParseNetPrototxtOrDie(edited, "edited", false, &ed);
+    EXPECT(ed.hidden.size() == 2 && ed.hidden[0] == 300 && ed.hidden[1] == 200 && ed.state_size == 77 && !ed.critic);
   }
   {  // NumStateFeatures (hfo_game.hpp:14-16)
     EXPECT(NumStateFeatures(1) == 59 && NumStateFeatures(3) == 77);

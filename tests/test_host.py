@@ -69,6 +69,25 @@ def test_dqn_main_benchmark_train_snapshot_resume(tmp_path):
     assert any(s.endswith(".solverstate") and "_actor_iter_" in s for s in snaps), snaps
     assert any(s.endswith(".caffemodel") and "_critic_iter_" in s for s in snaps), snaps
     assert any(s.endswith(".replaymemory") for s in snaps), snaps
+    # dqn_main.cpp:232-246: the nets of the run were written as <prefix>_{actor,critic}.prototxt ...
+    for kind, head in (("actor", "actionpara_layer"), ("critic", "q_values_layer")):
+        txt = open(prefix + f"_agent0_{kind}.prototxt").read()
+        assert 'type: "InnerProduct"' in txt and f'name: "{head}"' in txt and "num_output: 128" in txt
+    # ... and an existing (user-edited) file defines the tower: two layers of 96 and 64 instead of -hidden
+    prefix_p = str(tmp_path / "prun")
+    for kind in ("actor", "critic"):
+        txt = open(prefix + f"_agent0_{kind}.prototxt").read()
+        cut_a, cut_b = txt.index('layer {\n  name: "ip3_layer"'), txt.index('layer {\n  name: "' + ("action_layer" if kind == "actor" else "q_values_layer"))
+        txt = txt[:cut_a] + txt[cut_b:]
+        txt = txt.replace("num_output: 128", "num_output: 96").replace('bottom: "ip4"', 'bottom: "ip2"')
+        open(prefix_p + f"_agent0_{kind}.prototxt", "w").write(txt)
+    args_p = [a if not a.startswith("-save=") else f"-save={prefix_p}" for a in args]
+    out_p = subprocess.run(args_p, capture_output=True, text=True, timeout=600)
+    assert out_p.returncode == 0, out_p.stderr[-3000:]
+    S = 59
+    n_actor = (S * 96 + 96) + (96 * 64 + 64) + (64 * 4 + 4) + (64 * 6 + 6)
+    fa = sorted(glob.glob(prefix_p + "_agent0_actor_iter_*.caffemodel"))
+    assert fa and os.path.getsize(fa[-1]) == 8 + 4 + 8 + 4 * n_actor, (os.path.getsize(fa[-1]), n_actor)
     # -async_update: Update() enqueues and books the previous update's loss; the learner state must not change
     prefix_a = str(tmp_path / "arun")
     args_a = [a if not a.startswith("-save=") else f"-save={prefix_a}" for a in args] + ["-async_update"]
