@@ -2,6 +2,7 @@
 // Control flow, flags, RNG call order, log-line formats and error convention (CHECK/LOG(FATAL)
 // abort) follow the reference's src/dqn.cpp; the arithmetic is in libdqn_b200.so.
 #include "dqn.hpp"
+#include "caffe_proto.hpp"
 
 #include <dirent.h>
 #include <sys/stat.h>
@@ -42,6 +43,9 @@ DEFINE_int32(device, 0, "CUDA device ordinal");
 DEFINE_bool(host_sampling, false, "Draw minibatch indices on the host with std::mt19937 exactly like "
                                   "SampleTransitionsFromMemory (default: device Philox sampler)");
 DEFINE_double(init_std, 0.01, "Std of the gaussian weight filler (dqn.cpp:352)");
+DEFINE_bool(caffe_snapshots, false, "Write .caffemodel / .solverstate as Caffe protobufs (NetParameter / SolverState, what "
+                                    "Solver::Snapshot writes upstream) instead of this build's flat files.  Reading "
+                                    "detects either format");
 DEFINE_bool(async_update, false, "Update() enqueues the update and books the loss of the PREVIOUS one (dqnb_update_async / "
                                  "dqnb_results): episodes, AddTransitions and logging overlap the GPU work.  The sampled "
                                  "memories, weights and iteration counts are those of the blocking loop; only the "
@@ -202,6 +206,7 @@ DQN::DQN(caffe::SolverParameter &actor_solver_param, caffe::SolverParameter &cri
   if (actor_solver_param.net_param_.state_size > 0) CHECK_EQ(actor_solver_param.net_param_.state_size, state_size);
   if (critic_solver_param.net_param_.state_size > 0) CHECK_EQ(critic_solver_param.net_param_.state_size, state_size);
   CHECK_LE((int)hidden.size(), DQNB_MAX_HIDDEN);
+  hidden_ = hidden;
   c.n_hidden = (int)hidden.size();
   for (size_t i = 0; i < hidden.size(); ++i) c.hidden[i] = hidden[i];
   c.replay_capacity = replay_memory_capacity_;
@@ -371,7 +376,9 @@ void DQN::Update() {  // dqn.cpp:799-826
 }
 
 // ---- snapshots ----------------------------------------------------------------------------------
-// .caffemodel / .solverstate are Caffe protobufs upstream; here they are flat little-endian files:
+// .caffemodel / .solverstate are Caffe protobufs upstream (NetParameter / SolverState).  Both are read
+// (caffe_proto.cpp: a reference checkpoint loads as it is); written on request (-caffe_snapshots), the default
+// being flat little-endian files:
 //   caffemodel : "DQNBW001" int64 n, float w[n]            (Caffe learnable_params order)
 //   solverstate: "DQNBS001" int32 iter, int64 n, float m[n], float v[n], then the caffemodel payload
 static void write_blob(const std::string &f, const char *magic, int32_t iter, const std::vector<const std::vector<float> *> &arrs) {
@@ -397,22 +404,71 @@ static void read_blob(const std::string &f, const char *magic, int32_t *iter, st
   CHECK(in.good()) << "truncated file " << f;
 }
 
-static void snapshot_net(dqnb_handle_s *h, int net, const std::string &base) {
-  const int64_t n = dqnb_param_count(h, net);
+static std::string read_file(const std::string &f) {
+  std::ifstream in(f, std::ios::binary);
+  CHECK(in.good()) << "Invalid file: " << f;
+  std::stringstream ss;
+  ss << in.rdbuf();
+  return ss.str();
+}
+static void write_file(const std::string &f, const std::string &bytes) {
+  std::ofstream o(f, std::ios::binary);
+  CHECK(o.good()) << "cannot write " << f;
+  o.write(bytes.data(), (std::streamsize)bytes.size());
+}
+
+void DQN::snapshot_net(int net, const std::string &base) const {
+  const int64_t n = dqnb_param_count(h_, net);
   std::vector<float> w((size_t)n), m((size_t)n), v((size_t)n);
   int32_t iter = 0;
-  DQNB_OK(dqnb_get_params(h, net, w.data()));
-  DQNB_OK(dqnb_get_opt_state(h, net, m.data(), v.data(), &iter));
+  DQNB_OK(dqnb_get_params(h_, net, w.data()));
+  DQNB_OK(dqnb_get_opt_state(h_, net, m.data(), v.data(), &iter));
+  if (FLAGS_caffe_snapshots) {   // Solver::SnapshotToBinaryProto + SnapshotSolverStateToBinaryProto
+    const bool critic = net == DQNB_CRITIC;
+    write_file(base + ".caffemodel", caffe_proto::EncodeNet(caffe_proto::NetFromFlat(critic ? "Critic" : "Actor", state_size_, hidden_, critic, w.data())));
+    caffe_proto::SolverState st;
+    st.iter = iter;
+    st.learned_net = base + ".caffemodel";
+    st.history = caffe_proto::HistoryFromFlat(caffe_proto::ParamLayers(state_size_, hidden_, critic), m.data(), v.data());
+    write_file(base + ".solverstate", caffe_proto::EncodeSolverState(st));
+    return;
+  }
   write_blob(base + ".caffemodel", "DQNBW001", iter, {&w});
   write_blob(base + ".solverstate", "DQNBS001", iter, {&m, &v, &w});
+}
+
+// Net::CopyTrainedLayersFrom (dqn.cpp:529,:537): this build's flat file, or a Caffe NetParameter whose layers are
+// matched by name (layers the net does not have are ignored, layers the file does not have keep their weights)
+void DQN::load_weights(int net, const std::string &f) {
+  const std::string bytes = read_file(f);
+  const int64_t n = dqnb_param_count(h_, net);
+  std::vector<float> w((size_t)n);
+  if (bytes.size() >= 8 && std::memcmp(bytes.data(), "DQNBW001", 8) == 0) {
+    std::vector<std::vector<float>> a; int32_t it;
+    read_blob(f, "DQNBW001", &it, a, 1);
+    CHECK_EQ((int64_t)a[0].size(), n);
+    w = a[0];
+  } else {
+    caffe_proto::Net proto;
+    CHECK(caffe_proto::DecodeNet(bytes, &proto)) << f << " is neither a DQNBW001 file nor a Caffe NetParameter";
+    DQNB_OK(dqnb_get_params(h_, net, w.data()));
+    std::string err;
+    const bool critic = net == DQNB_CRITIC;
+    const int copied = caffe_proto::FlatFromNet(proto, state_size_, hidden_, critic, w.data(), &err);
+    CHECK_GE(copied, 0) << f << ": " << err;
+    LOG(INFO) << "Copied " << copied << " of " << caffe_proto::ParamLayers(state_size_, hidden_, critic).size()
+              << " parametrised layers from " << f << " (net \"" << proto.name << "\", " << proto.layers.size() << " layers)";
+  }
+  DQNB_OK(dqnb_set_params(h_, net, w.data()));
+  DQNB_OK(dqnb_set_params(h_, net + 2, w.data()));   // CloneNet: targets are re-cloned, not checkpointed (dqn.cpp:530,:538,:546,:555)
 }
 
 void DQN::Snapshot() { Snapshot(save_path_, FLAGS_remove_old_snapshots, FLAGS_snapshot_memory); }
 
 void DQN::Snapshot(const std::string &prefix, bool remove_old, bool snapshot_memory) {  // dqn.cpp:586-620
   const int ai = actor_iter(), ci = critic_iter();
-  snapshot_net(h_, DQNB_ACTOR, prefix + "_actor_iter_" + std::to_string(ai));
-  snapshot_net(h_, DQNB_CRITIC, prefix + "_critic_iter_" + std::to_string(ci));
+  snapshot_net(DQNB_ACTOR, prefix + "_actor_iter_" + std::to_string(ai));
+  snapshot_net(DQNB_CRITIC, prefix + "_critic_iter_" + std::to_string(ci));
   if (snapshot_memory) {
     const std::string mem = prefix + "_iter_" + std::to_string(max_iter()) + ".replaymemory";
     LOG(INFO) << "Snapshotting memory to " << mem;
@@ -427,35 +483,45 @@ void DQN::Snapshot(const std::string &prefix, bool remove_old, bool snapshot_mem
   LOG(INFO) << "Snapshotting Finished!";
 }
 
-void DQN::LoadActorWeights(const std::string &f) {  // dqn.cpp:525-531 (+ CloneNet)
-  std::vector<std::vector<float>> a; int32_t it;
-  read_blob(f, "DQNBW001", &it, a, 1);
-  CHECK_EQ((int64_t)a[0].size(), dqnb_param_count(h_, DQNB_ACTOR));
-  DQNB_OK(dqnb_set_params(h_, DQNB_ACTOR, a[0].data()));
-  DQNB_OK(dqnb_set_params(h_, DQNB_ACTOR_TARGET, a[0].data()));
-}
-void DQN::LoadCriticWeights(const std::string &f) {
-  std::vector<std::vector<float>> a; int32_t it;
-  read_blob(f, "DQNBW001", &it, a, 1);
-  CHECK_EQ((int64_t)a[0].size(), dqnb_param_count(h_, DQNB_CRITIC));
-  DQNB_OK(dqnb_set_params(h_, DQNB_CRITIC, a[0].data()));
-  DQNB_OK(dqnb_set_params(h_, DQNB_CRITIC_TARGET, a[0].data()));
-}
-static void restore_solver(dqnb_handle_s *h, int net, const std::string &f) {
-  std::vector<std::vector<float>> a; int32_t it;
-  read_blob(f, "DQNBS001", &it, a, 3);
-  CHECK_EQ((int64_t)a[0].size(), dqnb_param_count(h, net));
-  DQNB_OK(dqnb_set_params(h, net, a[2].data()));
-  DQNB_OK(dqnb_set_params(h, net + 2, a[2].data()));   // targets are re-cloned, not checkpointed (dqn.cpp:546,:555)
-  DQNB_OK(dqnb_set_opt_state(h, net, a[0].data(), a[1].data(), it));
+void DQN::LoadActorWeights(const std::string &f) { load_weights(DQNB_ACTOR, f); }    // dqn.cpp:525-531
+void DQN::LoadCriticWeights(const std::string &f) { load_weights(DQNB_CRITIC, f); }  // dqn.cpp:533-539
+
+// Solver::Restore (dqn.cpp:541-557): iteration + Adam history, weights from the model the state points to
+void DQN::restore_solver(int net, const std::string &f) {
+  const std::string bytes = read_file(f);
+  const int64_t n = dqnb_param_count(h_, net);
+  if (bytes.size() >= 8 && std::memcmp(bytes.data(), "DQNBS001", 8) == 0) {
+    std::vector<std::vector<float>> a; int32_t it;
+    read_blob(f, "DQNBS001", &it, a, 3);
+    CHECK_EQ((int64_t)a[0].size(), n);
+    DQNB_OK(dqnb_set_params(h_, net, a[2].data()));
+    DQNB_OK(dqnb_set_params(h_, net + 2, a[2].data()));   // targets are re-cloned, not checkpointed (dqn.cpp:546,:555)
+    DQNB_OK(dqnb_set_opt_state(h_, net, a[0].data(), a[1].data(), it));
+    return;
+  }
+  caffe_proto::SolverState st;
+  CHECK(caffe_proto::DecodeSolverState(bytes, &st)) << f << " is neither a DQNBS001 file nor a Caffe SolverState";
+  if (!st.learned_net.empty()) {
+    std::string model = st.learned_net;
+    if (!is_regular_file(model)) {   // snapshots moved to another directory: look beside the solver state
+      const size_t sl = f.find_last_of('/'), ml = model.find_last_of('/');
+      model = (sl == std::string::npos ? std::string() : f.substr(0, sl + 1)) + (ml == std::string::npos ? model : model.substr(ml + 1));
+    }
+    load_weights(net, model);
+  }
+  std::vector<float> m((size_t)n), v((size_t)n);
+  std::string err;
+  CHECK(caffe_proto::FlatFromHistory(st.history, caffe_proto::ParamLayers(state_size_, hidden_, net == DQNB_CRITIC), m.data(), v.data(), &err))
+      << f << ": " << err;
+  DQNB_OK(dqnb_set_opt_state(h_, net, m.data(), v.data(), st.iter));
 }
 void DQN::RestoreActorSolver(const std::string &f) {
   LOG(INFO) << "Actor solver state resuming from " << f;
-  restore_solver(h_, DQNB_ACTOR, f); iters_dirty_ = true; last_snapshot_iter_ = max_iter();
+  restore_solver(DQNB_ACTOR, f); iters_dirty_ = true; last_snapshot_iter_ = max_iter();
 }
 void DQN::RestoreCriticSolver(const std::string &f) {
   LOG(INFO) << "Critic solver state resuming from " << f;
-  restore_solver(h_, DQNB_CRITIC, f); iters_dirty_ = true; last_snapshot_iter_ = max_iter();
+  restore_solver(DQNB_CRITIC, f); iters_dirty_ = true; last_snapshot_iter_ = max_iter();
 }
 
 // Replay-memory file: the reference's gzip layout (dqn.cpp:1152-1173, kStateInputCount == 1):

@@ -125,6 +125,10 @@ class DQN {
   mutable int actor_iter_cache_, critic_iter_cache_;
   mutable bool iters_dirty_;
   std::pair<float, float> last_update_;
+  std::vector<int> hidden_;      // tower widths of both nets
+  void snapshot_net(int net, const std::string &base) const;
+  void load_weights(int net, const std::string &file);
+  void restore_solver(int net, const std::string &file);
   long long pending_step_ = 0;   // -async_update: sequence number of the update whose results are still to be read
 };
 

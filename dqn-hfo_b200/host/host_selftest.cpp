@@ -5,7 +5,9 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <vector>
 
+#include "caffe_proto.hpp"
 #include "dqn.hpp"
 #include "hfo_game.hpp"
 #include "shim/flags.hpp"
@@ -76,6 +78,83 @@ int main() {
     caffe::NetParameter ed;
     dqn::ParseNetPrototxtOrDie(edited, "edited", false, &ed);
     EXPECT(ed.hidden.size() == 2 && ed.hidden[0] == 300 && ed.hidden[1] == 200 && ed.state_size == 77 && !ed.critic);
+  }
+  {  // Caffe checkpoint files (caffe_proto.cpp): NetParameter / SolverState in protobuf wire format
+    namespace cp = caffe_proto;
+    const std::vector<int> hidden = {5, 3};
+    const int S = 4;
+    for (int critic = 0; critic < 2; ++critic) {
+      const std::vector<cp::ParamLayer> pl = cp::ParamLayers(S, hidden, critic != 0);
+      const long long n = cp::ParamCount(pl);
+      EXPECT(n == (critic ? (14 * 5 + 5) + (5 * 3 + 3) + (3 + 1) : (4 * 5 + 5) + (5 * 3 + 3) + (3 * 4 + 4) + (3 * 6 + 6)));
+      std::vector<float> w((size_t)n), m((size_t)n), v((size_t)n);
+      for (long long i = 0; i < n; ++i) { w[i] = 0.25f * (float)i - 3.f; m[i] = 1e-3f * (float)i; v[i] = 1e-6f * (float)(i * i); }
+      // weights: flat -> NetParameter bytes -> flat
+      const std::string bytes = cp::EncodeNet(cp::NetFromFlat(critic ? "Critic" : "Actor", S, hidden, critic != 0, w.data()));
+      cp::Net net;
+      EXPECT(cp::DecodeNet(bytes, &net));
+      EXPECT(net.name == (critic ? "Critic" : "Actor") && net.layers.size() == pl.size() + hidden.size());
+      EXPECT(net.layers[0].name == "ip1_layer" && net.layers[0].type == "InnerProduct" && net.layers[1].type == "ReLU");
+      EXPECT(net.layers[0].blobs.size() == 2 && net.layers[0].blobs[0].shape.size() == 2 && net.layers[0].blobs[0].shape[0] == 5);
+      std::vector<float> back((size_t)n, -7.f);
+      std::string err;
+      EXPECT(cp::FlatFromNet(net, S, hidden, critic != 0, back.data(), &err) == (int)pl.size());
+      EXPECT(back == w);
+      // CopyTrainedLayersFrom semantics: a layer missing from the file keeps its values, a foreign layer is ignored
+      cp::Net partial = net;
+      partial.layers.erase(partial.layers.begin());            // drop ip1_layer
+      cp::Layer foreign; foreign.name = "conv1"; foreign.type = "Convolution"; foreign.blobs.resize(1); foreign.blobs[0].data = {1.f, 2.f};
+      partial.layers.push_back(foreign);
+      std::vector<float> kept((size_t)n, 9.f);
+      EXPECT(cp::FlatFromNet(partial, S, hidden, critic != 0, kept.data(), &err) == (int)pl.size() - 1);
+      const long long first = (long long)pl[0].out * pl[0].in + pl[0].out;
+      bool ok = true;
+      for (long long i = 0; i < n; ++i) ok = ok && kept[i] == (i < first ? 9.f : w[i]);
+      EXPECT(ok);
+      // a known layer with the wrong shape is an error, not a silent skip
+      cp::Net bad = net;
+      bad.layers[0].blobs[0].data.pop_back();
+      EXPECT(cp::FlatFromNet(bad, S, hidden, critic != 0, kept.data(), &err) == -1 && err.find("ip1_layer") != std::string::npos);
+      // solver state: iter + Adam history (m for every blob, then v), learned_net path
+      cp::SolverState st;
+      st.iter = 123456; st.learned_net = "/tmp/x_actor_iter_123456.caffemodel"; st.history = cp::HistoryFromFlat(pl, m.data(), v.data());
+      cp::SolverState st2;
+      EXPECT(cp::DecodeSolverState(cp::EncodeSolverState(st), &st2));
+      EXPECT(st2.iter == 123456 && st2.learned_net == st.learned_net && st2.history.size() == 4 * pl.size() && st2.current_step == 0);
+      std::vector<float> m2((size_t)n), v2((size_t)n);
+      EXPECT(cp::FlatFromHistory(st2.history, pl, m2.data(), v2.data(), &err));
+      EXPECT(m2 == m && v2 == v);
+      st2.history.pop_back();
+      EXPECT(!cp::FlatFromHistory(st2.history, pl, m2.data(), v2.data(), &err));
+    }
+    // bytes assembled by hand from the protobuf encoding rules (independent of the encoder above):
+    // NetParameter{ name: "N", layer{ name: "q_values_layer", blobs{ shape{dim:[1,2]} data:[1.5,-2] }, blobs{ shape{dim:[1]} data:[0.5] } } }
+    // plus an unknown varint field (5: force_backward) and an unknown fixed32 field that must be skipped
+    auto f32 = [](float x) { std::string s(4, '\0'); std::memcpy(&s[0], &x, 4); return s; };
+    const std::string blob_w = std::string("\x3a\x04\x0a\x02\x01\x02", 6) + std::string("\x2a\x08", 2) + f32(1.5f) + f32(-2.f);
+    const std::string blob_b = std::string("\x3a\x03\x0a\x01\x01", 5) + std::string("\x2a\x04", 2) + f32(0.5f);
+    std::string layer = std::string("\x0a\x0e", 2) + "q_values_layer";
+    layer += std::string("\x3a", 1) + std::string(1, (char)blob_w.size()) + blob_w;
+    layer += std::string("\x3a", 1) + std::string(1, (char)blob_b.size()) + blob_b;
+    std::string hand = std::string("\x0a\x01N", 3) + std::string("\x28\x01", 2) + std::string("\x7d", 1) + f32(3.f);
+    hand += std::string("\xa2\x06", 2) + std::string(1, (char)layer.size()) + layer;
+    cp::Net hn;
+    EXPECT(cp::DecodeNet(hand, &hn));
+    EXPECT(hn.name == "N" && hn.layers.size() == 1 && hn.layers[0].name == "q_values_layer" && hn.layers[0].blobs.size() == 2);
+    EXPECT(hn.layers[0].blobs[0].shape == (std::vector<long long>{1, 2}) && hn.layers[0].blobs[0].data == (std::vector<float>{1.5f, -2.f}));
+    EXPECT(hn.layers[0].blobs[1].data == (std::vector<float>{0.5f}));
+    // the same layer in the pre-2015 V1 spelling: NetParameter.layers = 2, V1LayerParameter{ name = 4, blobs = 6 }, legacy dims
+    const std::string v1blob = std::string("\x08\x01\x10\x01\x18\x01\x20\x02", 8) + std::string("\x2a\x08", 2) + f32(1.5f) + f32(-2.f);
+    std::string v1layer = std::string("\x22\x0e", 2) + "q_values_layer" + std::string("\x32", 1) + std::string(1, (char)v1blob.size()) + v1blob;
+    const std::string v1net = std::string("\x12", 1) + std::string(1, (char)v1layer.size()) + v1layer;
+    cp::Net vn;
+    EXPECT(cp::DecodeNet(v1net, &vn));
+    EXPECT(vn.layers.size() == 1 && vn.layers[0].name == "q_values_layer" && vn.layers[0].blobs.size() == 1);
+    EXPECT(vn.layers[0].blobs[0].shape == (std::vector<long long>{1, 1, 1, 2}) && vn.layers[0].blobs[0].data.size() == 2);
+    // garbage is rejected, not mis-read
+    cp::Net gn;
+    EXPECT(!cp::DecodeNet(std::string("DQNBW001\x00\x00\x00\x00", 12), &gn) || gn.layers.empty());
+    EXPECT(!cp::DecodeNet(std::string("\xa2\x06\x7f", 3), &gn));     // layer length beyond the end of the buffer
   }
   {  // NumStateFeatures (hfo_game.hpp:14-16)
     EXPECT(NumStateFeatures(1) == 59 && NumStateFeatures(3) == 77);

@@ -107,3 +107,48 @@ def test_dqn_main_benchmark_train_snapshot_resume(tmp_path):
     its = [int(re.search(r"_actor_iter_(\d+)\.solverstate", s).group(1)) for s in
            (os.path.basename(p) for p in glob.glob(prefix + "_agent0_actor_iter_*.solverstate"))]
     assert max(its) >= 160
+
+
+@pytest.mark.gpu
+def test_dqn_main_caffe_protobuf_snapshots_resume(tmp_path):
+    """-caffe_snapshots: .caffemodel / .solverstate are written as Caffe NetParameter / SolverState protobufs
+    (what Solver::Snapshot writes upstream, dqn.cpp:589-590) and a run resumes from them (Solver::Restore +
+    CopyTrainedLayersFrom by layer name, dqn.cpp:541-557); the resumed learner continues from the same weights
+    as one resumed from the flat files of an identical run."""
+    build_host()
+    exe = os.path.join(HOST, "dqn")
+    common = ["-memory_threshold=64", "-memory=5000", "-explore=50", "-seed=5", "-loss_display_iter=50", "-update_ratio=1.0",
+              "-frames_per_trial=60", "-evaluate_freq=100000", "-snapshot_freq=100000", "-hidden=128,64,64,32"]
+    finals = {}
+    for tag, extra in (("flat", []), ("caffe", ["-caffe_snapshots"])):
+        prefix = str(tmp_path / tag)
+        out = subprocess.run([exe, f"-save={prefix}", "-max_iter=80"] + common + extra, capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stderr[-3000:]
+        model = sorted(glob.glob(prefix + "_agent0_actor_iter_*.caffemodel"))[-1]
+        raw = open(model, "rb").read()
+        if tag == "caffe":
+            assert raw[:2] == b"\x0a\x05" and raw[2:7] == b"Actor" and b"ip1_layer" in raw and b"actionpara_layer" in raw
+            state = open(model.replace(".caffemodel", ".solverstate"), "rb").read()
+            assert state[:1] == b"\x08" and os.path.basename(model).encode() in state     # iter varint, learned_net path
+        else:
+            assert raw[:8] == b"DQNBW001"
+        out2 = subprocess.run([exe, f"-save={prefix}", "-max_iter=110"] + common + extra, capture_output=True, text=True, timeout=600)
+        assert out2.returncode == 0, out2.stderr[-3000:]
+        assert "Actor solver state resuming from" in out2.stderr and "Critic solver state resuming from" in out2.stderr
+        its = [int(re.search(r"_critic_iter_(\d+)\.solverstate", os.path.basename(p)).group(1))
+               for p in glob.glob(prefix + "_agent0_critic_iter_*.solverstate")]
+        assert max(its) >= 110
+        finals[tag] = max(its)
+    # both formats carry the same state: the two resumed runs end at the same iteration with identical weights
+    assert finals["flat"] == finals["caffe"]
+    it = finals["flat"]
+    import struct
+    flat = open(str(tmp_path / "flat") + f"_agent0_critic_iter_{it}.caffemodel", "rb").read()
+    n = struct.unpack("<q", flat[12:20])[0]
+    w_flat = flat[20:20 + 4 * n]
+    caffe = open(str(tmp_path / "caffe") + f"_agent0_critic_iter_{it}.caffemodel", "rb").read()
+    # first parametrised blob of the protobuf = ip1_layer W: its packed float payload must equal the flat file's prefix
+    S, H1 = 59 + 10, 128
+    k = caffe.index(b"ip1_layer")
+    payload = w_flat[:4 * S * H1]
+    assert payload in caffe[k:], "ip1_layer weights differ between the flat and the protobuf checkpoint"
