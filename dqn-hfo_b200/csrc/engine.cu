@@ -231,7 +231,7 @@ struct SplitMat {           // [2][rows][ld] fp32 in HBM
 };
 
 struct Op {                 // one kernel launch of the update / act sequence
-  enum Kind { GEMM, GEMM_GROUP, GATHER, SAMPLE, HEAD_FWD, CRITIC_HEAD, ACTOR_HEAD_BWD, HEAD_BWD_W, COLSUM, REDUCE,
+  enum Kind { GEMM, GEMM_GROUP_UNUSED, GATHER, SAMPLE, HEAD_FWD, CRITIC_HEAD, ACTOR_HEAD_BWD, HEAD_BWD_W, COLSUM, REDUCE,
               ALLREDUCE, P2P_ALLREDUCE, ADAM, PREP, FINALIZE, FORK, JOIN } kind;
   int branch = 0;           // 0 = main stream; 1, 2 = side streams between FORK and JOIN
   int wait_ev = -1;         // event the op's stream waits for before the launch (cross-branch edge)
@@ -239,7 +239,6 @@ struct Op {                 // one kernel launch of the update / act sequence
   int mask = 3;             // FORK / JOIN: which side streams take part
   int variant = 0;          // 0: always; 1: only when indices are drawn on the device; 2: only when injected
   GemmArgs gemm; dim3 grid;
-  GroupArgs group;          // GEMM_GROUP: several GEMMs in one launch
   GatherArgs gather; HeadArgs head; CriticHeadArgs ch; ActorHeadBwdArgs ahb; HeadBwdWArgs hbw; ColsumArgs cs;
   ReduceArgs red; AdamArgs adam; P2PArgs p2p;
   float *ar_buf = nullptr; size_t ar_count = 0;
@@ -276,6 +275,9 @@ struct dqnb_handle_s {
   std::vector<void *> ipc_opened;
   int comm_mode = 0;                  // 0 none, 1 NCCL all-reduce, 2 P2P exchange kernel
   float *Gpart[2] = {nullptr, nullptr}; long long gpart_stride[2] = {0, 0};   // [actor, critic]
+  // bias-gradient partials [planes][bflat]: plane = 128-row block of the minibatch (written by the dX epilogue that
+  // produces the dZ tile) or row slice of colsum_kernel; boff[l] = offset of tower layer l inside a plane
+  float *Bpart[2] = {nullptr, nullptr}; long long bflat = 0; int bplanes = 0; long long boff[DQNB_MAX_HIDDEN] = {};
   float *norm_part = nullptr; int n_norm[2] = {0, 0};
   double *scal_part = nullptr; int n_scal = 0;
   // replay ring
@@ -358,9 +360,8 @@ static int env_int(const char *name, int dflt) {
 }
 struct Tuning {
   int sched;        // 0: three forward chains at once; 1: (target actor || critic) then (target critic || actor)
-  int dw0_main;     // 1: the last weight-gradient GEMM (layer 0) follows the dX chain on the main stream
-  int colsum_side;  // 1: bias column sums on side stream 1 beside that GEMM
-  int dw_streams;   // 1: every weight-gradient GEMM on its own side stream, per-layer bias column sums on stream 2
+  int fuse_colsum;  // 1: bias gradients of the layers below the top one come from the dX epilogues (0: colsum launches)
+  int fuse_tl;      // 1: TD target + critic loss head in one launch
   int cluster_b;    // 1: cluster split-K also for the target chains, which share the machine with the side chains
   int pdl_early;    // GEMM kernels: 1 = launch_dependents right after the wait, 0 = after the last MMA issue
   int bn_big;       // 128: dX / dW GEMMs that fill the machine with 128x64 tiles anyway use 128x128 tiles (half the CTAs,
@@ -369,9 +370,8 @@ struct Tuning {
   int st_fwd, st_fwd_side, st_dx, st_dw;   // smem ring depth per GEMM class (0 = deepest that fits)
   Tuning() {
     sched = env_int("DQNB_SCHED", 1);
-    dw0_main = env_int("DQNB_DW0_MAIN", 0);
-    colsum_side = env_int("DQNB_COLSUM_SIDE", 0);
-    dw_streams = env_int("DQNB_DW_STREAMS", 1);
+    fuse_colsum = env_int("DQNB_FUSE_COLSUM", 1);
+    fuse_tl = env_int("DQNB_FUSE_TL", 1);
     cluster_b = env_int("DQNB_CLUSTER_B", 0);
     pdl_early = env_int("DQNB_PDL_EARLY", 0);
     bn_big = env_int("DQNB_BN_BIG", 64);
@@ -551,9 +551,7 @@ static int launch_op(dqnb_handle_s *h, const Op &op, cudaStream_t s) {
       else
         e = launch_k(gemm_simt_kernel, op.grid, dim3(256), 0, s, op.gemm.p);
       break;
-    case Op::GEMM_GROUP:
-      e = launch_k(gemm_tc_grouped_kernel<1, 1, 64>, op.grid, dim3(TC_THREADS), (size_t)tc_smem_for(64, tc_max_stages(64)), s, op.group);
-      break;
+    case Op::GEMM_GROUP_UNUSED: break;
     case Op::GATHER: e = launch_k(gather_kernel, dim3(h->Bp), dim3(128), 0, s, op.gather); break;
     case Op::SAMPLE:
       e = launch_k(sample_kernel, dim3((h->B + 255) / 256), dim3(256), 0, s, (const StepState *)h->st,
@@ -647,90 +645,70 @@ static Op make_colsum(dqnb_handle_s *h, const NetGeom &g, int l0, int l1) {
   for (int l = l0; l < l1; ++l) {
     const int i = l - l0;
     a.dZ[i] = h->dZ[l].p; a.plane[i] = h->dZ[l].plane(); a.ld[i] = h->dZ[l].ld; a.Np[i] = g.L[l].Np;
-    a.b_off[i] = g.L[l].b_off; a.blk_begin[i] = blk; blk += (g.L[l].Np + kCsCols - 1) / kCsCols;
+    a.b_off[i] = h->boff[l]; a.blk_begin[i] = blk; blk += (g.L[l].Np + kCsCols - 1) / kCsCols;
   }
   a.blk_begin[l1 - l0] = blk;
-  a.gpart = h->Gpart[g.critic]; a.gpart_stride = h->gpart_stride[g.critic];
+  a.gpart = h->Bpart[g.critic]; a.gpart_stride = h->bflat;
   op.grid = dim3(blk, kGradSplits);
   return op;
 }
 
 // tower backward from dZ[top] (already masked by the head backward).  The dX chain is the critical
 // path and stays on the main stream.  With want_dw every weight-gradient GEMM runs on a side stream of its
-// own (branch 3 + l) and the head gradient + the last bias column sums on branch 2, each gated by an event on
-// the dZ it consumes, so a gradient starts the moment its dZ exists; all JOIN back before the reduction.
+// own (branch 3 + l) and the head gradient on branch 2, each gated by an event on the dZ it consumes, so a
+// gradient starts the moment its dZ exists; all JOIN back before the reduction.  Bias gradients (column sums of
+// dZ): the dX epilogue that produces dZ[l-1] also writes its per-row-block column sums (gemm.cuh); only the top
+// layer, whose dZ comes from a head kernel, keeps a colsum launch (behind its weight gradient).
 static int build_backward(dqnb_handle_s *h, const NetGeom &g, const float *P, const SplitMat &X,
                           SplitMat *acts, bool want_dw, SegTable *segs, const Op *head_bwd_w,
                           std::vector<Op> &ops) {
   const int top = g.n_hidden - 1;
   if (g.n_hidden + 1 > 8) DQNB_FAIL("too many layers for the event table");
-  const bool grouped_env = getenv("DQNB_GROUPED_DW") != nullptr;
-  const bool dws = want_dw && tuning().dw_streams && !grouped_env;
+  const bool fuse_cs = want_dw && h->cfg.gemm_mode == DQNB_GEMM_TCGEN05_3XTF32 && tuning().fuse_colsum;
   int fork_mask = 3;
-  if (dws) for (int l = 0; l <= top; ++l) fork_mask |= 1 << (2 + l);
+  if (want_dw) for (int l = 0; l <= top; ++l) fork_mask |= 1 << (2 + l);
   if (want_dw) {
     // the side streams pick up once dZ[top] exists
     Op f; f.kind = Op::FORK; f.mask = fork_mask; ops.push_back(f);
     if (head_bwd_w) { Op w = *head_bwd_w; w.branch = 2; ops.push_back(w); }
   }
-  // Experiment kept behind DQNB_GROUPED_DW=1: the weight-gradient GEMMs of all layers as ONE grouped launch
-  // after the dX chain.  Measured 2.75e6 vs 2.75-2.79e6 tr/s for the per-layer launches that overlap the
-  // chain on the side stream (the group is ~3 waves of CTAs that only start when the chain is done).
-  const bool grouped = want_dw && h->cfg.gemm_mode == DQNB_GEMM_TCGEN05_3XTF32 && g.n_hidden <= kMaxGroup && grouped_env;
-  Op grp;
-  grp.kind = Op::GEMM_GROUP;
-  grp.group.n = 0;
-  grp.group.tile_begin[0] = 0;
   for (int l = top; l >= 0; --l) {
     if (want_dw) {
       Op op;
       int splits = 1;
       if (op_dw(h->cfg, g, l, h->dZ[l], l > 0 ? acts[l - 1] : X, h->Gpart[g.critic], h->gpart_stride[g.critic], &splits, &op)) return -1;
-      op.branch = dws ? 3 + l : 1;
+      op.branch = 3 + l;
       if (l < top) op.wait_ev = l;                              // dZ[l] is produced by the dX op below
-      if (l == 0 && top > 0 && tuning().dw0_main && !grouped) {
-        // the last weight gradient only waits for the dX op right before it: on the main stream it starts with a
-        // programmatic hand-off instead of a cross-stream event (measured ~10 us later)
-        op.branch = 0; op.wait_ev = -1;
-      }
-      if (grouped) {
-        const int i = grp.group.n++;
-        grp.group.g[i] = op.gemm;
-        grp.group.tile_begin[i + 1] = grp.group.tile_begin[i] + (int)(op.grid.x * op.grid.y * op.grid.z);
-      } else {
-        ops.push_back(op);
-        // bias column sums of dZ[l] ride behind the weight gradient that waits for the same dZ; the last two
-        // (whose GEMMs form the tail of the pass) run beside their GEMMs on branch 2, after the head gradient
-        if (dws && (l > 1 || l == top)) { Op c = make_colsum(h, g, l, l + 1); c.branch = 3 + l; ops.push_back(c); }
+      ops.push_back(op);
+      const bool fused_here = fuse_cs && l < top;
+      if (!fused_here) {
+        // bias column sums of dZ[l] by a launch of their own: behind the weight gradient that waits for the same dZ;
+        // the last two (whose GEMMs form the tail of the pass) beside their GEMMs on branch 2, after the head gradient
+        Op c = make_colsum(h, g, l, l + 1);
+        if (l > 1 || l == top) c.branch = 3 + l; else { c.branch = 2; c.wait_ev = l; }
+        ops.push_back(c);
       }
       // segment table entries (internal flat order: W_l then b_l)
       SegTable &T = *segs;
       T.begin[2 * l] = g.L[l].w_off; T.end[2 * l] = g.L[l].b_off; T.nsplit[2 * l] = splits;
-      T.begin[2 * l + 1] = g.L[l].b_off; T.end[2 * l + 1] = g.L[l].b_off + g.L[l].Np; T.nsplit[2 * l + 1] = kGradSplits;
+      T.src[2 * l] = h->Gpart[g.critic] + g.L[l].w_off; T.stride[2 * l] = h->gpart_stride[g.critic];
+      T.begin[2 * l + 1] = g.L[l].b_off; T.end[2 * l + 1] = g.L[l].b_off + g.L[l].Np;
+      T.nsplit[2 * l + 1] = fused_here ? h->Bp / BM : kGradSplits;
+      T.src[2 * l + 1] = h->Bpart[g.critic] + h->boff[l]; T.stride[2 * l + 1] = h->bflat;
     }
     if (l > 0) {
       Op op;
       if (op_dx(h->cfg, g, l, P, h->dZ[l], acts[l - 1], h->dZ[l - 1], &op)) return -1;
       if (want_dw) op.rec_ev = l - 1;                           // dZ[l-1] ready
+      if (fuse_cs) { op.gemm.p.colsum_out = h->Bpart[g.critic] + h->boff[l - 1]; op.gemm.p.colsum_stride = h->bflat; }
       ops.push_back(op);
-      if (dws && l <= 2) { Op c = make_colsum(h, g, l - 1, l); c.branch = 2; c.wait_ev = l - 1; ops.push_back(c); }
     }
-  }
-  if (grouped) {
-    grp.branch = 1;
-    if (g.n_hidden > 1) grp.wait_ev = 0;                        // dZ[0] is the last one the chain produces
-    grp.grid = dim3(grp.group.tile_begin[grp.group.n]);
-    ops.push_back(grp);
   }
   if (want_dw) {
-    if (!dws) {
-      Op op = make_colsum(h, g, 0, g.n_hidden);                 // main stream: every dZ exists after the dX chain
-      if (tuning().colsum_side && top > 0) { op.branch = 1; op.wait_ev = 0; }   // beside the layer-0 weight gradient
-      ops.push_back(op);
-    }
     SegTable &T = *segs;
     const int hs = 2 * g.n_hidden;
     T.begin[hs] = g.hw_off; T.end[hs] = g.flat; T.nsplit[hs] = kGradSplits;   // head W, b (+ zero tail)
+    T.src[hs] = h->Gpart[g.critic] + g.hw_off; T.stride[hs] = h->gpart_stride[g.critic];
     T.n = hs + 1;
     Op j; j.kind = Op::JOIN; j.mask = fork_mask; ops.push_back(j);
   }
@@ -745,7 +723,7 @@ static void build_solver(dqnb_handle_s *h, int is_critic, const SegTable &segs, 
   r.kind = Op::REDUCE;
   ReduceArgs &a = r.red;
   memset(&a, 0, sizeof(a));
-  a.segs = segs; a.flat = g.flat; a.gpart = h->Gpart[is_critic]; a.gpart_stride = h->gpart_stride[is_critic];
+  a.segs = segs; a.flat = g.flat;
   a.G = h->G[is_critic]; a.norm_part = h->norm_part; a.scal_part = h->scal_part; a.n_scal = h->n_scal;
   a.scal_scale = scal_scale; a.do_reduce = 1; a.do_sumsq = multi ? 0 : 1;
   r.blocks = blocks;
@@ -872,10 +850,19 @@ static int build_update_ops(dqnb_handle_s *h) {
   op.rec_ev = -1;
   if (sched == 1 && push_actor_chain(2, kEvActorStart)) return -1;
   if (build_forward(h, gC, PCT, h->Xct, h->actCT, ops, true, tuning().cluster_b != 0)) return -1;
-  push_critic_head(h, QMODE_TARGET, PCT, h->actCT[topC], h->q_next, ops);   // dqn.cpp:892-900
-  op.kind = Op::JOIN; op.mask = fork_mask; ops.push_back(op);
-  // rest of critic_solver_->Step(1): loss, backward, clip, Adam (+ soft update of the target critic)
-  push_critic_head(h, QMODE_LOSS, PC, h->actC[topC], h->q, ops);
+  if (tuning().fuse_tl) {
+    // dqn.cpp:892-900 TD target and the head of critic_solver_->Step(1) (loss + head backward) in one launch
+    op.kind = Op::JOIN; op.mask = fork_mask; ops.push_back(op);
+    push_critic_head(h, QMODE_TARGET_LOSS, PC, h->actC[topC], h->q, ops);
+    CriticHeadArgs &a = ops.back().ch;
+    a.H2 = h->actCT[topC].p; a.h2_plane = h->actCT[topC].plane();
+    a.W2 = PCT + gC.hw_off; a.w2_plane = gC.flat; a.bias2 = PCT + gC.hb_off; a.b2_plane = gC.flat; a.q_tap2 = h->q_next;
+  } else {
+    push_critic_head(h, QMODE_TARGET, PCT, h->actCT[topC], h->q_next, ops);   // dqn.cpp:892-900
+    op.kind = Op::JOIN; op.mask = fork_mask; ops.push_back(op);
+    // rest of critic_solver_->Step(1): loss, backward, clip, Adam (+ soft update of the target critic)
+    push_critic_head(h, QMODE_LOSS, PC, h->actC[topC], h->q, ops);
+  }
   Op hbw = make_head_bwd_w(h, gC, h->d16c, h->actC[topC]);
   if (build_backward(h, gC, PC, h->Xc, h->actC, true, &h->segs[1], &hbw, ops)) return -1;
   build_solver(h, 1, h->segs[1], 0.5f * h->hp.inv_batch_global, ops);
@@ -1065,6 +1052,10 @@ static int create_impl(const dqnb_config *cfg, dqnb_handle_s *h) {
   }
   h->gpart_stride[0] = fA; h->gpart_stride[1] = fC;
   if (dalloc(h, &h->Gpart[0], (size_t)kGradSplits * fA) || dalloc(h, &h->Gpart[1], (size_t)kGradSplits * fC)) return -1;
+  h->bflat = 0;
+  for (int l = 0; l < c.n_hidden; ++l) { h->boff[l] = h->bflat; h->bflat += h->gA.L[l].Np; }
+  h->bplanes = std::max((int)kGradSplits, h->Bp / BM);
+  if (dalloc(h, &h->Bpart[0], (size_t)h->bplanes * h->bflat) || dalloc(h, &h->Bpart[1], (size_t)h->bplanes * h->bflat)) return -1;
   if (dalloc(h, &h->norm_part, (size_t)(fmax / 1024))) return -1;
   h->n_scal = (h->Bp + kHeadRowsPerBlock - 1) / kHeadRowsPerBlock;     // one loss / avg-q partial per critic_head block
   if (dalloc(h, &h->scal_part, (size_t)h->n_scal)) return -1;
@@ -1514,12 +1505,12 @@ int dqnb_benchmark_gemms(dqnb_handle h, int32_t reps, float *ms_per_update, int3
   if (!h || reps <= 0 || !ms_per_update) DQNB_FAIL("bad argument");
   DQNB_CUDA(cudaSetDevice(h->cfg.device));
   int n = 0;
-  for (const Op &op : h->update_ops) if (op.kind == Op::GEMM || op.kind == Op::GEMM_GROUP) ++n;
+  for (const Op &op : h->update_ops) if (op.kind == Op::GEMM) ++n;
   DQNB_CUDA(cudaStreamSynchronize(h->stream));
   for (int r = 0; r < reps + 2; ++r) {
     if (r == 2) DQNB_CUDA(cudaEventRecord(h->ev0, h->stream));
     for (const Op &op : h->update_ops)
-      if ((op.kind == Op::GEMM || op.kind == Op::GEMM_GROUP) && launch_op(h, op, h->stream)) return -1;
+      if (op.kind == Op::GEMM && launch_op(h, op, h->stream)) return -1;
   }
   DQNB_CUDA(cudaEventRecord(h->ev1, h->stream));
   DQNB_CUDA(cudaEventSynchronize(h->ev1));

@@ -40,6 +40,10 @@ struct GemmParams {
   // EPI_FWD writes it next to the activation, EPI_DX reads 4 bytes per 32 columns instead of 256
   // (the fp32 mask tile was 64 KB of LSU loads per CTA competing with the TMA operand stream).
   uint32_t *relu_bits_out; const uint32_t *relu_bits_in; int ldbits;
+  // tcgen05 kernel, EPI_DX: the bias gradient of the layer below is the column sum of the dZ tile this epilogue
+  // produces (Caffe: gemv(dY^T, ones)).  Each CTA adds its 128 rows and writes one partial row:
+  // colsum_out[m_tile * colsum_stride + n]; reduce_kernel sums the m_tile planes in fixed order (nullable).
+  float *colsum_out; long long colsum_stride;
   int apply_lrelu;                            // EPI_FWD: 0 for linear layers
   int bn;                                     // N tile of the tcgen05 kernel: 64 or 128
   int stages;                                 // depth of the TMA->MMA smem ring (2..4).  BN=64 with 2 stages is 98 KB
@@ -182,7 +186,7 @@ struct TcCfg {
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;   // 48 / 64 KB
   static constexpr int MAX_STAGES = (TC_SMEM_MAX - 2048) / STAGE_BYTES > 4 ? 4 : (TC_SMEM_MAX - 2048) / STAGE_BYTES;
   static constexpr int MIN_STAGES = 2;          // also holds the epilogue's staging boxes (4 warps x BN/32 x 8 KB)
-  static constexpr int smem_bytes(int stages) { return stages * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 512 /*bias tile*/; }
+  static constexpr int smem_bytes(int stages) { return stages * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 512 /*bias tile*/ + 4 * BN_ * 4 /*column sums*/; }
   static constexpr int TMEM_COLS = 2 * BN_;                    // two fp32 accumulators of BN columns
 };
 constexpr int MN_GROUP_BYTES = 2 * 32 * BK * 4;       // MN-major: one 32-wide group, hi plane then lo plane
@@ -466,6 +470,7 @@ __device__ __forceinline__ void gemm_tc_body(const GemmArgs &args, const int n_t
     const int q = warp & 3;                  // TMEM lane quarter this warp may read
     const int half = warp >> 2;
     float *s_bias = reinterpret_cast<float *>(base_ptr + STAGES * Cfg::STAGE_BYTES + 256);
+    float *s_colsum = s_bias + 128;          // [4 row quarters][BN]
     float *st_hi = reinterpret_cast<float *>(base_ptr) + (q * 32) * LDS;
     const int n_base = n_tile * BN_;
     const bool peer = clus && crank == 1;
@@ -572,6 +577,7 @@ __device__ __forceinline__ void gemm_tc_body(const GemmArgs &args, const int n_t
                 bits_out |= (x > 0.f ? 1u : 0u) << (j + t);            // sign of the in-place activation
               } else {
                 x *= ((bits_in >> (j + t)) & 1u) ? 1.f : kNegSlope;    // ReLU backward on the in-place activation
+                v[j + t] = x;                                          // kept for the column sum below
               }
               o[t] = tf32_hi(x);
               l[t] = x - o[t];
@@ -582,6 +588,25 @@ __device__ __forceinline__ void gemm_tc_body(const GemmArgs &args, const int n_t
           }
           if (p.epi == EPI_FWD && p.relu_bits_out && m_row < p.M && n_base + c0 < p.N)
             p.relu_bits_out[(long long)m_row * p.ldbits + ((n_base + c0) >> 5)] = bits_out;
+          if (p.epi == EPI_DX && p.colsum_out) {
+            // column sums over this warp's 32 rows: halving butterfly, 31 shuffles; lane L ends up with column c0 + L
+            // (bit b of the lane selects bit b of the column).  Fixed tree -> the same bits on every run.
+            if (m_row >= p.M) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = 0.f;
+            }
+#pragma unroll
+            for (int sft = 16; sft >= 1; sft >>= 1) {
+              const bool upper = (lane & sft) != 0;
+#pragma unroll
+              for (int j = 0; j < sft; ++j) {
+                const float send = upper ? v[j] : v[j + sft];
+                const float keep = upper ? v[j + sft] : v[j];
+                v[j] = keep + __shfl_xor_sync(0xffffffffu, send, sft);
+              }
+            }
+            s_colsum[q * BN_ + c0 + lane] = v[0];
+          }
         }
         // hand this chunk's box (both planes) to the TMA unit; the next chunk is staged meanwhile
         fence_proxy_async_smem();
@@ -589,6 +614,13 @@ __device__ __forceinline__ void gemm_tc_body(const GemmArgs &args, const int n_t
         if (lane == 0 && n_base + c0 < p.N && m_tile * BM + q * 32 < p.M) {
           tma_store_3d(&args.tmD, box - row_off, n_base + c0, m_tile * BM + q * 32, planes_out == 1 ? split : 0);
           bulk_commit();
+        }
+      }
+      if (p.epi == EPI_DX && p.colsum_out) {
+        asm volatile("bar.sync 2, %0;" ::"n"(TC_THREADS) : "memory");   // every warp of this (non-peer) CTA is here
+        if (threadIdx.x < BN_ && n_base + (int)threadIdx.x < p.N) {
+          const float *c = s_colsum + threadIdx.x;
+          p.colsum_out[(long long)m_tile * p.colsum_stride + n_base + threadIdx.x] = ((c[0] + c[BN_]) + c[2 * BN_]) + c[3 * BN_];
         }
       }
       if (lane == 0) bulk_wait_all();          // the boxes have been read and written before shared memory goes away
@@ -619,26 +651,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
   gemm_tc_body<A_MN, B_MN, BN_>(args, blockIdx.x, blockIdx.y, blockIdx.z);
 }
 
-// Grouped launch: several independent GEMMs (the four weight-gradient GEMMs of one backward pass) share one
-// grid, so they cost one launch and fill the machine together.  blockIdx.x enumerates the tiles of all
-// members; the tensor maps stay in the (grid-constant) parameter space.
-constexpr int kMaxGroup = 4;
-struct alignas(64) GroupArgs {
-  GemmArgs g[kMaxGroup];
-  int n;
-  int tile_begin[kMaxGroup + 1];
-};
-template <int A_MN, int B_MN, int BN_>
-__global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_grouped_kernel(const __grid_constant__ GroupArgs ga) {
-  int i = 0;
-  const int t = blockIdx.x;
-  while (i + 1 < ga.n && t >= ga.tile_begin[i + 1]) ++i;
-  const GemmArgs &args = ga.g[i];
-  const int local = t - ga.tile_begin[i];
-  const int nt = (args.p.N + BN_ - 1) / BN_, mt = (args.p.M + BM - 1) / BM;
-  gemm_tc_body<A_MN, B_MN, BN_>(args, local % nt, (local / nt) % mt, local / (nt * mt));
-}
-
 // host-side dispatch over the template instances
 typedef void (*TcKernel)(const GemmArgs);
 inline TcKernel tc_kernel_for(int a_mn, int b_mn, int bn) {
@@ -662,10 +674,6 @@ inline cudaError_t tc_prepare(const void *fn, int bn) {
   return cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 inline cudaError_t tc_prepare_all() {
-  {
-    cudaError_t e = tc_prepare((const void *)gemm_tc_grouped_kernel<1, 1, 64>, 64);
-    if (e != cudaSuccess) return e;
-  }
   for (int bn : {64, 128})
     for (int a = 0; a < 2; ++a)
       for (int b = 0; b < 2; ++b) {

@@ -271,15 +271,20 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const HeadArgs a) {
 //   POLICY: dq = -1 (dqn.cpp:918-921), avg-q partial sum q
 //   LOSS/POLICY also write the head backward into the tower top, masked by that layer's ReLU':
 //   dZ[n][k] = dq * w_q[k] * relu'(h[n][k])
-enum { QMODE_TARGET = 0, QMODE_LOSS = 1, QMODE_POLICY = 2 };
+//   TARGET_LOSS: both of the above in one launch (the target tower's top activation H2 / head W2 give y, then the
+//   online tower's H / W the loss): one kernel boundary less on the critical chain of the update
+enum { QMODE_TARGET = 0, QMODE_LOSS = 1, QMODE_POLICY = 2, QMODE_TARGET_LOSS = 3 };
 struct CriticHeadArgs {
   long long *trace;              // DQNB_TRACE timeline slot (nullable)
   int mode, B, rows_pad;
   const float *H; long long h_plane; int ldh; int Kp;
   const float *W; long long w_plane; const float *bias; long long b_plane;
+  // TARGET_LOSS only: the target critic's top activation and head (H / W above are the online critic's)
+  const float *H2; long long h2_plane; const float *W2; long long w2_plane; const float *bias2; long long b2_plane;
+  float *q_tap2;               // TARGET_LOSS: q_next
   const float *reward, *mc, *term;
-  float *y;                    // TARGET: out ; LOSS: in
-  float *q_tap;                // TARGET: q_next ; LOSS: q ; POLICY: q_pi
+  float *y;                    // TARGET: out ; LOSS: in ; TARGET_LOSS: out (tap)
+  float *q_tap;                // TARGET: q_next ; LOSS / TARGET_LOSS: q ; POLICY: q_pi
   float *d16;                  // LOSS: dq for the head weight gradient (column 0 of [rows][16])
   float *dZ; long long dz_plane;
   double *part;                // per-block partial: LOSS sum (q-y)^2 ; POLICY sum q
@@ -300,6 +305,18 @@ __global__ void __launch_bounds__(256) critic_head_kernel(const CriticHeadArgs a
       for (int k = lane * 4; k < a.Kp; k += 128)
         acc = dot4(add4(ld4(hh + k), ld4(hh + k + a.h_plane)), add4(ld4(a.W + k), ld4(a.W + k + a.w_plane)), acc);
       const float q = warp_sum(acc) + (a.bias[0] + a.bias[a.b_plane]);
+      float y_here = 0.f;
+      if (a.mode == QMODE_TARGET_LOSS) {
+        const float *h2 = a.H2 + (long long)n * a.ldh;
+        float acc2 = 0.f;
+        for (int k = lane * 4; k < a.Kp; k += 128)
+          acc2 = dot4(add4(ld4(h2 + k), ld4(h2 + k + a.h2_plane)), add4(ld4(a.W2 + k), ld4(a.W2 + k + a.w2_plane)), acc2);
+        const float qn = warp_sum(acc2) + (a.bias2[0] + a.bias2[a.b2_plane]);
+        const bool terminal = a.term[n] != 0.f;
+        const float off = terminal ? a.reward[n] : (float)((double)a.reward[n] + a.hp.gamma * (double)qn);
+        y_here = (float)(a.hp.beta * (double)a.mc[n] + (1 - a.hp.beta) * (double)off);
+        if (lane == 0) { a.y[n] = y_here; a.q_tap2[n] = terminal ? 0.f : qn; }
+      }
       if (a.mode == QMODE_TARGET) {
         if (lane == 0) {
           const bool terminal = a.term[n] != 0.f;
@@ -308,8 +325,8 @@ __global__ void __launch_bounds__(256) critic_head_kernel(const CriticHeadArgs a
           a.y[n] = (float)(a.hp.beta * (double)a.mc[n] + (1 - a.hp.beta) * (double)off);
           a.q_tap[n] = terminal ? 0.f : q;
         }
-      } else if (a.mode == QMODE_LOSS) {
-        const float diff = q - a.y[n];
+      } else if (a.mode == QMODE_LOSS || a.mode == QMODE_TARGET_LOSS) {
+        const float diff = q - (a.mode == QMODE_LOSS ? a.y[n] : y_here);
         dq = __fmul_rn(a.hp.inv_batch_global, diff);
         if (lane == 0) { a.d16[(long long)n * 16] = dq; a.q_tap[n] = q; contrib = (double)diff * (double)diff; }
       } else {
@@ -507,12 +524,15 @@ struct SegTable {
   int n;
   long long begin[kMaxSegs], end[kMaxSegs];
   int nsplit[kMaxSegs];
+  // where the partial planes of a segment live: plane p of parameter i at src[s] + p * stride[s] + (i - begin[s]).
+  // Weight gradients: the split-K planes of the dW GEMMs; bias gradients: one plane per 128-row block of the
+  // minibatch, written by the epilogue that produced dZ (gemm.cuh EPI_DX) or by colsum_kernel.
+  const float *src[kMaxSegs]; long long stride[kMaxSegs];
 };
 struct ReduceArgs {
   long long *trace;              // DQNB_TRACE timeline slot (nullable)
   SegTable segs;
   long long flat;
-  const float *gpart; long long gpart_stride;
   float *G;                    // [flat + 4]; tail[0] carries the scalar of this pass
   float *norm_part;            // per-block sum of squares
   const double *scal_part; int n_scal; float scal_scale;   // tail[0] = scale * sum(scal_part)
@@ -529,16 +549,20 @@ __global__ void __launch_bounds__(256) reduce_kernel(const ReduceArgs a) {
       int s = 0;
       while (s + 1 < a.segs.n && i >= a.segs.end[s]) ++s;
       const int ns = a.segs.nsplit[s];
-      // every plane's load is issued before the first add (a load-add-load-add loop is one L2 round trip per
-      // plane); the summation order stays plane 0, 1, 2, ..
-      float4 t[kGradSplits];
+      const float *src = a.segs.src[s] + (i - a.segs.begin[s]);
+      const long long stride = a.segs.stride[s];
+      // every plane's load (of a batch of kGradSplits) is issued before the first add (a load-add-load-add loop is
+      // one L2 round trip per plane); the summation order stays plane 0, 1, 2, ..
+      g = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int p0 = 0; p0 < ns; p0 += kGradSplits) {
+        float4 t[kGradSplits];
 #pragma unroll
-      for (int p = 0; p < kGradSplits; ++p)
-        if (p < ns) t[p] = *reinterpret_cast<const float4 *>(a.gpart + (long long)p * a.gpart_stride + i);
-      g = t[0];
+        for (int p = 0; p < kGradSplits; ++p)
+          if (p0 + p < ns) t[p] = *reinterpret_cast<const float4 *>(src + (long long)(p0 + p) * stride);
 #pragma unroll
-      for (int p = 1; p < kGradSplits; ++p)
-        if (p < ns) { g.x += t[p].x; g.y += t[p].y; g.z += t[p].z; g.w += t[p].w; }
+        for (int p = 0; p < kGradSplits; ++p)
+          if (p0 + p < ns) { g.x += t[p].x; g.y += t[p].y; g.z += t[p].z; g.w += t[p].w; }
+      }
       *reinterpret_cast<float4 *>(a.G + i) = g;
     } else {
       g = *reinterpret_cast<const float4 *>(a.G + i);

@@ -43,9 +43,9 @@ DEFINE_int32(device, 0, "CUDA device ordinal");
 DEFINE_bool(host_sampling, false, "Draw minibatch indices on the host with std::mt19937 exactly like "
                                   "SampleTransitionsFromMemory (default: device Philox sampler)");
 DEFINE_double(init_std, 0.01, "Std of the gaussian weight filler (dqn.cpp:352)");
-DEFINE_bool(caffe_snapshots, false, "Write .caffemodel / .solverstate as Caffe protobufs (NetParameter / SolverState, what "
-                                    "Solver::Snapshot writes upstream) instead of this build's flat files.  Reading "
-                                    "detects either format");
+DEFINE_bool(caffe_snapshots, true, "Write .caffemodel / .solverstate as Caffe protobufs (NetParameter / SolverState, what "
+                                   "Solver::Snapshot writes upstream).  -nocaffe_snapshots writes this build's flat "
+                                   "DQNBW001 / DQNBS001 files instead.  Reading detects either format");
 DEFINE_bool(async_update, false, "Update() enqueues the update and books the loss of the PREVIOUS one (dqnb_update_async / "
                                  "dqnb_results): episodes, AddTransitions and logging overlap the GPU work.  The sampled "
                                  "memories, weights and iteration counts are those of the blocking loop; only the "
@@ -210,7 +210,7 @@ DQN::DQN(caffe::SolverParameter &actor_solver_param, caffe::SolverParameter &cri
   c.n_hidden = (int)hidden.size();
   for (size_t i = 0; i < hidden.size(); ++i) c.hidden[i] = hidden[i];
   c.replay_capacity = replay_memory_capacity_;
-  c.max_act_batch = std::max(batch_size_ < 128 ? batch_size_ : 128, 1);
+  c.max_act_batch = std::max(batch_size_, 1);   // SelectActions accepts up to batch_size_ states (dqn.cpp:699)
   c.gamma = FLAGS_gamma; c.beta = FLAGS_beta; c.tau = (float)FLAGS_tau; c.soft_update_freq = FLAGS_soft_update_freq;
   CHECK(actor_solver_param.type() == "Adam" && critic_solver_param.type() == "Adam") << "only the Adam solver is implemented";
   c.actor_lr = actor_solver_param.base_lr(); c.critic_lr = critic_solver_param.base_lr();
@@ -222,7 +222,19 @@ DQN::DQN(caffe::SolverParameter &actor_solver_param, caffe::SolverParameter &cri
   DQNB_OK(dqnb_init_params(h_, seed, (float)FLAGS_init_std));
 }
 
-DQN::~DQN() { dqnb_destroy(h_); }
+DQN::~DQN() {
+  drain_pending();
+  dqnb_destroy(h_);
+}
+
+// -async_update: the loss of the last enqueued update has not been looked at yet (dqn.cpp:906 checks every one)
+void DQN::drain_pending() {
+  if (pending_step_ <= 0) return;
+  float loss = 0.f, avg_q = 0.f;
+  DQNB_OK(dqnb_results(h_, pending_step_, 1, &loss, &avg_q));
+  pending_step_ = 0;
+  CHECK(std::isfinite(loss)) << "Critic loss not finite!";
+}
 
 void DQN::refresh_iters() const {
   if (!iters_dirty_) return;
@@ -237,6 +249,7 @@ void DQN::ClearReplayMemory() { DQNB_OK(dqnb_clear_memory(h_)); }
 
 void DQN::Benchmark(int iterations) {  // dqn.cpp:487-498
   LOG(INFO) << "*** Benchmark begins ***";
+  drain_pending();
   float ms = 0.f;
   DQNB_OK(dqnb_benchmark(h_, iterations, &ms));
   iters_dirty_ = true;
@@ -390,7 +403,7 @@ static void write_blob(const std::string &f, const char *magic, int32_t iter, co
   o.write((const char *)&n, 8);
   for (auto *a : arrs) o.write((const char *)a->data(), sizeof(float) * a->size());
 }
-static void read_blob(const std::string &f, const char *magic, int32_t *iter, std::vector<std::vector<float>> &arrs, int count) {
+static void read_blob(const std::string &f, const char *magic, int32_t *iter, std::vector<std::vector<float>> &arrs, int count, int64_t expect_n) {
   std::ifstream in(f, std::ios::binary);
   CHECK(in.good()) << "Invalid file: " << f;
   char m[8];
@@ -399,6 +412,7 @@ static void read_blob(const std::string &f, const char *magic, int32_t *iter, st
   in.read((char *)iter, 4);
   int64_t n = 0;
   in.read((char *)&n, 8);
+  CHECK(in.good() && n == expect_n) << f << " holds " << n << " parameters, this net has " << expect_n;
   arrs.assign(count, std::vector<float>((size_t)n));
   for (auto &a : arrs) in.read((char *)a.data(), sizeof(float) * n);
   CHECK(in.good()) << "truncated file " << f;
@@ -445,7 +459,7 @@ void DQN::load_weights(int net, const std::string &f) {
   std::vector<float> w((size_t)n);
   if (bytes.size() >= 8 && std::memcmp(bytes.data(), "DQNBW001", 8) == 0) {
     std::vector<std::vector<float>> a; int32_t it;
-    read_blob(f, "DQNBW001", &it, a, 1);
+    read_blob(f, "DQNBW001", &it, a, 1, n);
     CHECK_EQ((int64_t)a[0].size(), n);
     w = a[0];
   } else {
@@ -466,6 +480,7 @@ void DQN::load_weights(int net, const std::string &f) {
 void DQN::Snapshot() { Snapshot(save_path_, FLAGS_remove_old_snapshots, FLAGS_snapshot_memory); }
 
 void DQN::Snapshot(const std::string &prefix, bool remove_old, bool snapshot_memory) {  // dqn.cpp:586-620
+  drain_pending();
   const int ai = actor_iter(), ci = critic_iter();
   snapshot_net(DQNB_ACTOR, prefix + "_actor_iter_" + std::to_string(ai));
   snapshot_net(DQNB_CRITIC, prefix + "_critic_iter_" + std::to_string(ci));
@@ -492,7 +507,7 @@ void DQN::restore_solver(int net, const std::string &f) {
   const int64_t n = dqnb_param_count(h_, net);
   if (bytes.size() >= 8 && std::memcmp(bytes.data(), "DQNBS001", 8) == 0) {
     std::vector<std::vector<float>> a; int32_t it;
-    read_blob(f, "DQNBS001", &it, a, 3);
+    read_blob(f, "DQNBS001", &it, a, 3, n);
     CHECK_EQ((int64_t)a[0].size(), n);
     DQNB_OK(dqnb_set_params(h_, net, a[2].data()));
     DQNB_OK(dqnb_set_params(h_, net + 2, a[2].data()));   // targets are re-cloned, not checkpointed (dqn.cpp:546,:555)
@@ -591,6 +606,9 @@ void DQN::LoadReplayMemory(const std::string &filename) {
   LOG(INFO) << "replay_mem_size = " << memory_size() << " with " << episodes << " episodes";
 }
 
+void DQN::ShareLayer(caffe::Layer<float> &, caffe::Layer<float> &) {
+  LOG(FATAL) << "ShareLayer (dqn.cpp:1037-1046) takes Caffe layer objects, which do not exist in this build; use ShareParameters";
+}
 void DQN::ShareParameters(DQN &, int, int) {
   LOG(FATAL) << "ShareParameters (dqn.cpp:1048-1079) is outside the hot-path scope of this build (SURVEY 8f-3)";
 }

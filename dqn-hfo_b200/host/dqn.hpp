@@ -4,26 +4,30 @@
 // this class owns one opaque dqnb_handle (include/dqn_b200.h): replay memory, weights, Adam state
 // and target nets live in HBM and every FLOP runs in libdqn_b200.so.
 //
-// Differences forced by the environment (no Boost/Caffe/glog/gflags in the image):
-//   boost::optional -> std::optional; caffe::SolverParameter/NetParameter -> shim/caffe_types.hpp;
-//   kMinibatchSize stays the reference's compile-time default but the minibatch actually used is
-//   the run-time flag -batch_size (BASELINE configs need 1024/4096/8192).
+// The reference's own src/dqn_main.cpp compiles against this header UNMODIFIED (host/Makefile target `dqn`,
+// tests/test_host.py): the same includes resolve to the stand-ins under shim/ (<boost/optional.hpp> is
+// std::optional, <caffe/caffe.hpp> the two protobuf messages of the interface as plain structs, glog / gflags
+// look-alikes, <HFO.hpp> an in-process environment), because Boost, Caffe, glog, gflags and libhfo are not in
+// this image.  kMinibatchSize stays the reference's compile-time default but the minibatch actually used
+// is the run-time flag -batch_size (BASELINE configs need 1024/4096/8192).
 #ifndef DQN_HPP_
 #define DQN_HPP_
 
 #include <HFO.hpp>
+#include <caffe/caffe.hpp>
+#include <boost/functional/hash.hpp>
+#include <boost/optional.hpp>
 #include <array>
 #include <deque>
 #include <memory>
 #include <mutex>
-#include <optional>
 #include <random>
 #include <string>
 #include <tuple>
+#include <unordered_map>
 #include <vector>
 
 #include "hfo_game.hpp"
-#include "shim/caffe_types.hpp"
 
 struct dqnb_handle_s;
 
@@ -51,7 +55,9 @@ using ActorOutput = std::array<float, kActionSize + kActionParamSize>;
 using StateData = std::vector<float>;
 using StateDataSp = std::shared_ptr<StateData>;
 using InputStates = std::array<StateDataSp, kStateInputCount>;
-using Transition = std::tuple<InputStates, ActorOutput, float, float, std::optional<StateDataSp>>;
+using Transition = std::tuple<InputStates, ActorOutput, float, float, boost::optional<StateDataSp>>;
+using SolverSp = std::shared_ptr<caffe::Solver<float>>;
+using NetSp = boost::shared_ptr<caffe::Net<float>>;
 
 class DQN {
  public:
@@ -88,7 +94,8 @@ class DQN {
   void SnapshotReplayMemory(const std::string &filename);               // dqn.cpp:1146-1178
   int memory_size() const;
 
-  // Multi-agent sharing (dqn.cpp:1037-1083) is outside the hot-path scope.
+  // Multi-agent sharing (dqn.cpp:1037-1083)
+  void ShareLayer(caffe::Layer<float> &param_owner, caffe::Layer<float> &param_slave);
   void ShareParameters(DQN &other, int num_actor_layers_to_share, int num_critic_layers_to_share);
   void ShareReplayMemory(DQN &other);
 
@@ -129,6 +136,7 @@ class DQN {
   void snapshot_net(int net, const std::string &base) const;
   void load_weights(int net, const std::string &file);
   void restore_solver(int net, const std::string &file);
+  void drain_pending();
   long long pending_step_ = 0;   // -async_update: sequence number of the update whose results are still to be read
 };
 

@@ -16,6 +16,7 @@
 #include <sstream>
 
 #include "dqn.hpp"
+#include "shim/flags.hpp"
 #include "shim/logging.hpp"
 
 namespace dqn {
@@ -291,3 +292,21 @@ void ReadNetPrototxtOrDie(const std::string &filename, bool critic, caffe::NetPa
 }
 
 }  // namespace dqn
+
+// The two Caffe helpers dqn_main.cpp:233-246 calls on <prefix>_{actor,critic}.prototxt.  Which of the two nets a
+// file describes is read off its layers (only the critic has a q_values_layer).
+namespace dqn { DECLARE_int32(batch_size); }
+namespace caffe {
+void ReadProtoFromTextFileOrDie(const char *filename, NetParameter *proto) {
+  std::ifstream f(filename);
+  CHECK(f.good()) << "Failed to open " << filename;
+  std::stringstream ss;
+  ss << f.rdbuf();
+  const std::string text = ss.str();
+  const bool critic = text.find(std::string("\"") + dqn::q_values_layer_name + "\"") != std::string::npos;
+  dqn::ParseNetPrototxtOrDie(text, filename, critic, proto);
+}
+void WriteProtoToTextFile(const NetParameter &proto, const char *filename) {
+  dqn::WriteNetPrototxt(proto, filename, dqn::FLAGS_batch_size);
+}
+}  // namespace caffe

@@ -40,7 +40,7 @@ class HFOEnvironment {
   void reset_episode();
   void fill_features();
   int num_features_ = 59, frames_per_trial_ = 500, unum_ = 11, frame_ = 0;
-  bool fresh_ = true;
+  bool fresh_ = true, configured_ = false;
   float px_, py_, heading_, bx_, by_, bvx_, bvy_;
   action_t pending_ = NOOP;
   float arg1_ = 0.f, arg2_ = 0.f;

@@ -1,4 +1,4 @@
-// caffe_types.hpp — plain-struct stand-ins for the two Caffe protobuf messages that appear in the
+// caffe_types.hpp (included through <caffe/caffe.hpp>) — plain-struct stand-ins for the two Caffe protobuf messages that appear in the
 // reference's public signatures (dqn.hpp:58-60, :204-205).  Only the fields dqn_main.cpp:229-262
 // fills are present; accessor names follow protobuf's generated API so caller code reads the same.
 #pragma once
@@ -16,6 +16,7 @@ struct NetParameter {
   const std::string &name() const { return name_; }
   void set_name(const std::string &n) { name_ = n; }
   void set_force_backward(bool b) { force_backward_ = b; }
+  void CopyFrom(const NetParameter &other) { *this = other; }
 };
 
 struct SolverParameter {

@@ -26,6 +26,7 @@ inline bool set_flag(const std::string &name, const std::string &value) {
 }
 // returns the number of arguments consumed as flags; unknown flags abort like gflags does
 int ParseCommandLineFlags(int *argc, char ***argv, bool remove_flags);
+int int_flag_or(const char *name, int dflt);
 }  // namespace shim
 
 namespace gflags { using shim::ParseCommandLineFlags; }

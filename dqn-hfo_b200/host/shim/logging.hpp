@@ -4,6 +4,7 @@
 #include <cstdlib>
 #include <iostream>
 #include <sstream>
+#include <utility>
 
 namespace shim {
 extern int g_vlog_level;
@@ -27,6 +28,11 @@ class LogMessage {
   int sev_;
 };
 struct Voidify { void operator&(std::ostream &) {} };
+template <typename T>
+T check_notnull(const char *file, int line, const char *what, T &&p) {   // glog's CHECK_NOTNULL: returns its argument
+  if (p == nullptr) LogMessage(file, line, FATAL).stream() << "Check failed: " << what;
+  return std::forward<T>(p);
+}
 }  // namespace shim
 
 #define LOG(sev) ::shim::LogMessage(__FILE__, __LINE__, ::shim::sev).stream()

@@ -4,11 +4,42 @@
 #include <iostream>
 
 #include "HFO.hpp"
+#include "caffe/caffe.hpp"
 #include "flags.hpp"
+#include "gflags/gflags.h"
+#include "glog/logging.h"
 #include "logging.hpp"
+
+// knobs of the in-process environment (the real ones are arguments of the HFO server: hfo_game.cpp:13)
+DEFINE_int32(frames_per_trial, 500, "Episode length cap of the in-process HFO stand-in (--frames-per-trial upstream)");
+DEFINE_int32(env_seed, 1, "Seed of the in-process HFO stand-in");
+
+namespace fLI { int FLAGS_logbuflevel = 0; }
+
+namespace gflags {
+static std::string g_usage, g_version;
+void SetUsageMessage(const std::string &usage) { g_usage = usage; }
+void SetVersionString(const std::string &version) { g_version = version; }
+const char *ProgramUsage() { return g_usage.c_str(); }
+}  // namespace gflags
+
+namespace caffe {
+static Caffe::Brew g_mode = Caffe::GPU;
+void Caffe::set_mode(Brew mode) {
+  if (mode == CPU && g_mode != CPU) LOG(WARNING) << "Caffe::set_mode(CPU) ignored: the update path of this build runs on the GPU only";
+  g_mode = mode;
+}
+Caffe::Brew Caffe::mode() { return g_mode; }
+}  // namespace caffe
 
 namespace shim {
 int g_vlog_level = 0;
+
+// value of an int32 flag that another translation unit DEFINEd (e.g. the caller's -offense_agents), or dflt
+int int_flag_or(const char *name, int dflt) {
+  auto it = flag_registry().find(name);
+  return (it != flag_registry().end() && it->second.type == 'i') ? *static_cast<int32_t *>(it->second.ptr) : dflt;
+}
 
 int ParseCommandLineFlags(int *argc, char ***argv, bool remove_flags) {
   int kept = 1, used = 0;
@@ -62,10 +93,19 @@ HFOEnvironment::HFOEnvironment() : rng_(1) { feat_.assign(num_features_, 0.f); r
 
 void HFOEnvironment::configure(int num_features, int frames_per_trial, unsigned seed) {
   num_features_ = num_features; frames_per_trial_ = frames_per_trial; rng_.seed(seed);
+  configured_ = true;
   feat_.assign(num_features_, 0.f);
   reset_episode();
 }
-void HFOEnvironment::connectToServer(feature_set_t, std::string, int, std::string, std::string, bool, std::string) {}
+// The real server tells the agent how many players are on the pitch; here the caller's own flags do
+// (dqn_main.cpp:52-58: NumStateFeatures = 50 + 9 * players, hfo_game.hpp:14-16).
+void HFOEnvironment::connectToServer(feature_set_t, std::string, int, std::string, std::string, bool, std::string) {
+  int players = 0;
+  for (const char *f : {"offense_agents", "offense_npcs", "offense_dummies", "defense_agents", "defense_npcs", "defense_dummies",
+                        "defense_chasers"})
+    players += shim::int_flag_or(f, 0);
+  if (players > 0 && !configured_) configure(50 + 9 * players, FLAGS_frames_per_trial, (unsigned)FLAGS_env_seed);
+}
 
 void HFOEnvironment::reset_episode() {
   std::uniform_real_distribution<float> ux(0.05f, 0.3f), uy(-0.3f, 0.3f), ua(-3.14159f, 3.14159f);

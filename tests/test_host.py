@@ -1,5 +1,6 @@
-"""The C++ host mirror (dqn-hfo_b200/host): builds with g++, its CPU self-test passes, and on the
-GPU the dqn_main look-alike trains, logs the reference's log lines, snapshots and resumes."""
+"""The C++ host mirror (dqn-hfo_b200/host): builds with g++, its CPU self-test passes, the REFERENCE's own
+src/dqn_main.cpp compiles unmodified against the mirror headers (host/Makefile target `dqn`), and on the GPU that
+binary benchmarks, trains, logs the reference's log lines, snapshots and resumes."""
 import glob
 import os
 import re
@@ -24,6 +25,27 @@ def test_host_mirror_builds_and_cpu_selftest_passes():
     assert "host_selftest: ok" in out.stdout
 
 
+def test_reference_dqn_main_compiles_unmodified_against_the_mirror():
+    """Drop-in proof: /root/reference/src/dqn_main.cpp, byte for byte, is the translation unit behind
+    host/dqn.  Where the reference tree is not mounted (the GPU box) the prebuilt binary is what is checked."""
+    build_host()
+    exe = os.path.join(HOST, "dqn")
+    assert os.access(exe, os.X_OK)
+    ref = "/root/reference/src/dqn_main.cpp"
+    if os.path.exists(ref):
+        link = os.path.join(HOST, "_ref", "dqn_main.cpp")
+        assert os.path.islink(link) and os.path.realpath(link) == os.path.realpath(ref)
+        assert os.path.getmtime(os.path.join(HOST, "_ref", "dqn_main.o")) >= os.path.getmtime(ref)
+        assert not os.path.exists(os.path.join(HOST, "dqn_main.cpp")), "the mirror must not carry its own dqn_main"
+    # the reference's main() refuses to run without -save / -evaluate (dqn_main.cpp:400-404), with its own message
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 1 and "Save path (or evaluate) required but not set." in out.stderr
+    strings = subprocess.run(["strings", exe], capture_output=True, text=True).stdout
+    for flag_help in ("Ratio of new experiences to updates.", "Shares replay memory between agents.",
+                      "Number of chasers playing defense"):          # dqn_main.cpp:47,:51,:59 flag table
+        assert flag_help in strings, flag_help
+
+
 def test_host_headers_keep_the_reference_api_surface():
     """Every public member / free function of the reference's dqn.hpp:56-242 and hfo_game.hpp:7-60 that
     is in scope must exist under the same name in the mirror headers."""
@@ -31,11 +53,12 @@ def test_host_headers_keep_the_reference_api_surface():
     for name in ["Benchmark", "RestoreActorSolver", "RestoreCriticSolver", "LoadActorWeights", "LoadCriticWeights",
                  "LoadReplayMemory", "Snapshot", "GetRandomActorOutput", "SelectAction", "SelectActions", "SampleAction",
                  "EvaluateAction", "AddTransition", "AddTransitions", "LabelTransitions", "Update", "ClearReplayMemory",
-                 "SnapshotReplayMemory", "memory_size", "ShareParameters", "ShareReplayMemory", "min_iter", "max_iter",
+                 "SnapshotReplayMemory", "memory_size", "ShareLayer", "ShareParameters", "ShareReplayMemory", "min_iter", "max_iter",
                  "critic_iter", "actor_iter", "state_size", "save_path", "unum", "set_unum", "CreateActorNet",
                  "CreateCriticNet", "GetAction", "FilesMatchingRegexp", "RemoveFilesMatchingRegexp", "RemoveSnapshots",
                  "FindLatestSnapshot", "FindHiScore", "PrintActorOutput", "kStateInputCount", "kMinibatchSize",
-                 "kActionSize", "kActionParamSize", "ActorOutput", "StateDataSp", "InputStates", "Transition"]:
+                 "kActionSize", "kActionParamSize", "ActorOutput", "StateDataSp", "InputStates", "Transition", "SolverSp",
+                 "NetSp", "boost::optional"]:
         assert re.search(r"\b%s\b" % name, dqn_hpp), name
     game_hpp = open(os.path.join(HOST, "hfo_game.hpp")).read()
     for name in ["struct Action", "NumStateFeatures", "kPassVelThreshold", "StartHFOServer", "StartDummyTeammate",
@@ -49,7 +72,7 @@ def test_dqn_main_benchmark_train_snapshot_resume(tmp_path):
     build_host()
     exe = os.path.join(HOST, "dqn")
     # -benchmark (dqn_main.cpp:332-338 -> DQN::Benchmark dqn.cpp:487-498)
-    out = subprocess.run([exe, "-benchmark", "-batch_size=1024", "-benchmark_iters=100", "-memory=20000", "-seed=3",
+    out = subprocess.run([exe, "-benchmark", f"-save={tmp_path / 'bench'}", "-batch_size=1024", "-memory=20000", "-seed=3",
                           "-frames_per_trial=2000"], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     m = re.search(r"Average Update: ([0-9.eE+-]+) ms", out.stderr)
@@ -58,7 +81,7 @@ def test_dqn_main_benchmark_train_snapshot_resume(tmp_path):
     prefix = str(tmp_path / "run")
     args = [exe, f"-save={prefix}", "-max_iter=120", "-memory_threshold=64", "-memory=5000", "-explore=50", "-seed=5",
             "-loss_display_iter=50", "-update_ratio=1.0", "-frames_per_trial=60", "-evaluate_freq=100000",
-            "-snapshot_freq=100000", "-hidden=128,64,64,32"]
+            "-snapshot_freq=100000", "-hidden=128,64,64,32", "-nocaffe_snapshots"]
     out = subprocess.run(args, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-3000:]
     log = out.stderr
@@ -111,7 +134,7 @@ def test_dqn_main_benchmark_train_snapshot_resume(tmp_path):
 
 @pytest.mark.gpu
 def test_dqn_main_caffe_protobuf_snapshots_resume(tmp_path):
-    """-caffe_snapshots: .caffemodel / .solverstate are written as Caffe NetParameter / SolverState protobufs
+    """Default snapshots: .caffemodel / .solverstate are written as Caffe NetParameter / SolverState protobufs
     (what Solver::Snapshot writes upstream, dqn.cpp:589-590) and a run resumes from them (Solver::Restore +
     CopyTrainedLayersFrom by layer name, dqn.cpp:541-557); the resumed learner continues from the same weights
     as one resumed from the flat files of an identical run."""
@@ -120,7 +143,7 @@ def test_dqn_main_caffe_protobuf_snapshots_resume(tmp_path):
     common = ["-memory_threshold=64", "-memory=5000", "-explore=50", "-seed=5", "-loss_display_iter=50", "-update_ratio=1.0",
               "-frames_per_trial=60", "-evaluate_freq=100000", "-snapshot_freq=100000", "-hidden=128,64,64,32"]
     finals = {}
-    for tag, extra in (("flat", []), ("caffe", ["-caffe_snapshots"])):
+    for tag, extra in (("flat", ["-nocaffe_snapshots"]), ("caffe", [])):
         prefix = str(tmp_path / tag)
         out = subprocess.run([exe, f"-save={prefix}", "-max_iter=80"] + common + extra, capture_output=True, text=True, timeout=600)
         assert out.returncode == 0, out.stderr[-3000:]
