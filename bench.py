@@ -139,8 +139,8 @@ def cpu_oracle_time(S, B, hidden, n_updates, seed=2, use_blas=True, threads=None
     from oracle import oracle as O
     O.build()
     blas = bool(use_blas and O.load_blas())
-    if threads:
-        O.lib().dqo_set_threads(threads)
+    # torchrun exports OMP_NUM_THREADS=1, which OpenBLAS honours at load time: ask for every host core explicitly
+    O.lib().dqo_set_threads(int(threads or os.cpu_count() or 1))
     ocfg = O.make_config(state_size=S, batch=B, hidden=hidden, caffe_wasted_work=1, use_blas=1 if blas else 0)
     rng = np.random.default_rng(seed)
     a0, c0 = O.init_params(ocfg, False, rng, "caffe"), O.init_params(ocfg, True, rng, "caffe")
@@ -164,6 +164,8 @@ def run_reference(args):
     S, hidden = args.state_size, tuple(args.hidden)
     B = args.batch
     probe, blas, cores = cpu_oracle_time(S, B, hidden, 1)
+    from oracle import oracle as O
+    O.lib().dqo_set_threads(int(os.cpu_count() or 1))
     # bound the whole run to ~2 minutes: shrink the per-step sample if needed
     budget = 120.0
     total_steps = args.steps + args.warmup
@@ -213,6 +215,48 @@ def workload_config(args, world):
     }
 
 
+def measure_tensor_peaks(torch):
+    """Dense TF32 and bf16 matmul throughput of this GPU through torch (cuBLAS), 8192^3, a short sustained loop:
+    the denominators of `frac_of_3xtf32_ceiling` (BASELINE.md section 3 asks for the TF32 peak to be measured)."""
+    out = {}
+    torch.backends.cuda.matmul.allow_tf32 = True
+    for name, dt in (("tf32", torch.float32), ("bf16", torch.bfloat16)):
+        a = torch.randn(8192, 8192, device="cuda", dtype=dt)
+        b = torch.randn(8192, 8192, device="cuda", dtype=dt)
+        for _ in range(3):
+            a @ b
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n = 60 if name == "tf32" else 120
+        e0.record()
+        for _ in range(n):
+            a @ b
+        e1.record()
+        torch.cuda.synchronize()
+        out[name + "_tflops_sustained"] = 2 * 8192 ** 3 * n / (e0.elapsed_time(e1) * 1e-3) / 1e12
+        del a, b
+    return out
+
+
+def act_latency(d, states, busy_updates=0):
+    """Wall-clock microseconds of one SelectActions call through the C-ABI with host buffers (median of 200 calls);
+    busy_updates > 0: while that many asynchronous updates are in flight on the learner's stream."""
+    out = {}
+    for n in (1, 8, 64):
+        x = np.ascontiguousarray(states[:n])
+        for _ in range(20):
+            d.select_actions(x)
+        last = d.update_async(busy_updates) if busy_updates else 0
+        ts = []
+        for _ in range(200):
+            t0 = time.perf_counter()
+            d.select_actions(x)
+            ts.append(time.perf_counter() - t0)
+        if busy_updates:
+            d.results(last, 1)
+        out[str(n)] = round(float(np.median(ts)) * 1e6, 2)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -225,6 +269,8 @@ def main():
     ap.add_argument("--replay", type=int, default=1_000_000)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the parity / wide-MLP / act-path / peak legs (profiling runs)")
+    ap.add_argument("--windows", type=int, default=3, help="timed windows of --steps updates each; the median is reported")
     ap.add_argument("--gemm-mode", type=int, default=0)
     ap.add_argument("--comm", default="p2p", choices=["p2p", "nccl"], help="gradient exchange for --gpus > 1")
     args = ap.parse_args()
@@ -242,31 +288,23 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
-    dist = None
+    dist = cpu_group = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        cpu_group = dist.new_group(backend="gloo")      # host-side waits that must not spin on the GPU
+    # NVML is initialised here, long before the timed region: nvmlInit() inside it skewed the ranks' start (round 1)
+    sampler = ClockSampler(local)
     S, B, hidden = args.state_size, args.batch, tuple(args.hidden)
-    rows = max(args.replay // world, 4 * B)
-    d = pkg.DQNB(device=local, state_size=S, batch=B, hidden=hidden, replay_capacity=rows + B + 8,
-                 seed=3 + rank, world_size=world, rank=rank, gemm_mode=args.gemm_mode, max_act_batch=64)
-    if world > 1 and args.comm == "nccl":
-        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            idt.copy_(torch.frombuffer(bytearray(pkg.comm_unique_id()), dtype=torch.uint8))
-        dist.broadcast(idt, 0)
-        d.comm_init(bytes(idt.cpu().numpy().tobytes()))
-    elif world > 1:   # product path: fused reduce-scatter + all-gather kernel over NVLink peer memory (CUDA IPC)
-        mine = torch.frombuffer(bytearray(d.comm_p2p_handle()), dtype=torch.uint8).cuda()
-        allh = [torch.empty_like(mine) for _ in range(world)]
-        dist.all_gather(allh, mine)
-        d.comm_p2p_init(b"".join(bytes(t.cpu().numpy().tobytes()) for t in allh))
-    d.init_params(seed=2, std=0.01)      # identical replicas: same seed on every rank
-    s, a, r, mc, term, sn = synth_replay(rows, S, seed=1 + rank)
-    for i in range(0, rows, 65536):
-        j = min(rows, i + 65536)
-        d.add_transitions(s[i:j], a[i:j], r[i:j], mc[i:j], sn[i:j], term[i:j])
-    d.sync()
+    from scripts import dp_parity
+
+    def make_learner(hid, rows, seed_off=0):
+        d = pkg.DQNB(device=local, state_size=S, batch=B, hidden=hid, replay_capacity=rows + B + 8,
+                     seed=3 + rank + seed_off, world_size=world, rank=rank, gemm_mode=args.gemm_mode, max_act_batch=64)
+        if world > 1:
+            dp_parity.connect(pkg, d, args.comm, rank, world, dist, torch)
+        d.init_params(seed=2, std=0.01)      # identical replicas: same seed on every rank
+        return d
 
     def barrier():
         torch.cuda.synchronize()
@@ -274,21 +312,42 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-timed value ------------------------------------------------------------------
+    def timed_window(d, steps):
+        """One timed window: ranks leave the barrier, run one untimed update (with N > 1 its gradient exchange
+        re-aligns the ranks on the device), then exactly `steps` updates between two CUDA events; max over ranks."""
+        barrier()
+        d.update(1)
+        torch.cuda.synchronize()
+        ms = d.benchmark(steps)
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- parity of this very configuration before anything is timed (N > 1: the driver's scaling runs carry it) ----
+    parity = None
+    if not args.no_extras and (world > 1 or os.environ.get("DQNB_BENCH_PARITY")):
+        parity = dp_parity.check(pkg, dist, torch, rank, world, local, S, B, hidden, comm=args.comm, n_updates=2)
+
+    rows = max(args.replay // world, 4 * B)
+    d = make_learner(hidden, rows)
+    s, a, r, mc, term, sn = synth_replay(rows, S, seed=1 + rank)
+    for i in range(0, rows, 65536):
+        j = min(rows, i + 65536)
+        d.add_transitions(s[i:j], a[i:j], r[i:j], mc[i:j], sn[i:j], term[i:j])
+    d.sync()
+
+    # ---- device-timed value: median of `windows` windows of exactly K steps ----------------------------
     d.update(args.warmup)
     barrier()
-    sampler = ClockSampler(local)
     sampler.start()
     l0 = d.kernel_launches()
-    ms = d.benchmark(args.steps)
-    launches = d.kernel_launches() - l0
+    windows = [timed_window(d, args.steps) for _ in range(max(1, args.windows))]
+    launches = round((d.kernel_launches() - l0) / (len(windows) * (args.steps + 1)) * args.steps)   # kernels inside one timed window
     sampler.stop_flag = True
     sampler.join()
     barrier()
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
+    ms_max = float(np.median(windows))
     value = B * world * args.steps / (ms_max * 1e-3)
 
     # ---- e2e through the C-ABI with host buffers ----------------------------------------------
@@ -297,7 +356,7 @@ def main():
     # host-mapped result ring (dqnb_results) while the current one runs - the learner loop of a caller
     # that logs its loss one step late.  All results are in host memory when the clock stops.  The
     # strictly blocking variant (dqnb_update returns the loss of the same step) is reported beside it.
-    e2e_steps = min(args.steps, 500)
+    e2e_steps = args.steps
     fresh = synth_replay(B * 8, S, seed=100 + rank)
 
     def add_rows(k):
@@ -308,12 +367,14 @@ def main():
     d.update(3)
     barrier()
     t0 = time.perf_counter()
-    for k in range(e2e_steps):
+    for k in range(min(e2e_steps, 500)):
         add_rows(k)
         loss, avgq = d.update(1)
     d.sync()
-    dt_sync = time.perf_counter() - t0
+    dt_sync = (time.perf_counter() - t0) / min(e2e_steps, 500)
     barrier()
+    d.update(1)
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
     step = 0
     for k in range(e2e_steps):
@@ -323,12 +384,12 @@ def main():
             loss, avgq = d.results(step - 1, 1)
     loss, avgq = d.results(step, 1)
     d.sync()
-    dt = time.perf_counter() - t0
+    dt = (time.perf_counter() - t0) / e2e_steps
     t = torch.tensor([dt, dt_sync], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_val = B * world * e2e_steps / float(t[0].item())
-    e2e_sync_val = B * world * e2e_steps / float(t[1].item())
+    e2e_val = B * world / float(t[0].item())
+    e2e_sync_val = B * world / float(t[1].item())
     Sp = (S + 63) // 64 * 64
     h2d = B * (2 * Sp + 16) * 4 + 8 + 4
     d2h = 8
@@ -338,13 +399,56 @@ def main():
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (3xTF32 tensor-core products, fp32 accumulate)",
         "data": "synthetic", "config": workload_config(args, world), "clocks": sampler.result(),
+        "windows_ms_per_step": [w / args.steps for w in windows],
         "e2e": {"value": e2e_val, "unit": "transitions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "blocking_value": e2e_sync_val,
+                # an end-to-end loop cannot be faster than its device-timed core: anything above ~1.02 flags a skewed window
+                "over_device_value": e2e_val / value,
                 "what": "per step: dqnb_add_transitions(B host rows -> pinned -> H2D on the copy stream) + dqnb_update_async(1) + "
                         "dqnb_results of the previous step (host-mapped result ring); blocking_value = same loop with dqnb_update(1)"},
         "gpu_launches": int(launches),
         "final": {"critic_loss": float(loss[-1]), "avg_q": float(avgq[-1])},
     }
+    if parity is not None:
+        line["parity"] = parity
+
+    # ---- extras: wide-MLP (BASELINE cfg5 per-GPU shape), act path, measured tensor peaks ----------------
+    peaks = None
+    if not args.no_extras:
+        wide_hidden = (1024, 1024, 1024, 1024)
+        wrows = 65536
+        dw = make_learner(wide_hidden, wrows, seed_off=100)
+        ws = synth_replay(wrows, S, seed=50 + rank)
+        dw.add_transitions(ws[0], ws[1], ws[2], ws[3], ws[5], ws[4])
+        dw.update(20)
+        wsteps = min(args.steps, 300)
+        wms = timed_window(dw, wsteps)
+        wfpt = flop_per_transition(S, wide_hidden)
+        line["wide_mlp"] = {
+            "workload": f"cfg5 per-GPU shape: 1024x4 towers, batch {B} per GPU, global batch {B * world}",
+            "value": B * world * wsteps / (wms * 1e-3), "unit": "transitions/s", "ms_per_step": wms / wsteps, "steps": wsteps,
+            "achieved_tflops_over_step_per_gpu": wfpt * B / (wms / wsteps * 1e-3) / 1e12,
+        }
+        if rank == 0:
+            try:
+                gms, ng = gemm_only_time(pkg, dw, reps=20)
+                line["wide_mlp"]["gemm_launches_per_step"] = ng
+                line["wide_mlp"]["gemm_achieved_tflops"] = wfpt * B / (gms * 1e-3) / 1e12
+            except Exception as e:
+                line["wide_mlp"]["gemm_error"] = str(e)
+        barrier()
+        dw.close()
+        if rank == 0:
+            line["act_path"] = {
+                "unit": "us per dqnb_select_actions call (host rows in, host rows out; median of 200)",
+                "rows": [1, 8, 64], "idle": act_latency(d, s), "while_updating": act_latency(d, s, busy_updates=300),
+                "what": "skinny-M kernels on the act stream reading the actor snapshot; never waits for the learner's stream",
+            }
+            try:
+                peaks = measure_tensor_peaks(torch)
+            except Exception as e:
+                peaks = {"error": str(e)}
+
     if rank == 0:
         hbm, bf16_burst, bf16_sus, src = measured_peaks()
         fpt = flop_per_transition(S, hidden)
@@ -358,15 +462,28 @@ def main():
                 "traffic": traffic, "traffic_source": traffic_src, "peak_source": f"{src} bf16_tflops_sustained (kernel timed inside a long step)",
                 "kernel": "dqnb::gemm_tc_kernel", "launches_per_step": n_gemm, "avg_launch_us": 1e3 * gemm_ms / n_gemm,
                 "algorithmic_flop_per_step": fpt * B,
-                "note": "3xTF32 issues 6 bf16-equivalent MMA passes per algorithmic product: ceiling = peak/6",
-                "frac_of_3xtf32_ceiling": ach / (bf16_sus / 6.0),
+                "note": "3xTF32 issues 3 TF32 MMA passes per algorithmic product: ceiling = measured TF32 peak / 3 "
+                        "(live torch/cuBLAS 8192^3 measurement below; bf16 peak / 6 when it is unavailable)",
                 # the same FLOP over the whole update (the GEMMs of independent branches overlap inside the step)
                 "achieved_over_step": fpt * B / (ms_max / args.steps * 1e-3) / 1e12,
                 "share_of_step": gemm_ms / (ms_max / args.steps),
             }
+            tf32 = (peaks or {}).get("tf32_tflops_sustained")
+            ceil3 = tf32 / 3.0 if tf32 else bf16_sus / 6.0
+            line["roofline"]["tf32_peak_measured"] = tf32
+            line["roofline"]["ceiling_3xtf32"] = ceil3
+            line["roofline"]["frac_of_3xtf32_ceiling"] = ach / ceil3
+            line["roofline"]["frac_of_3xtf32_ceiling_over_step"] = line["roofline"]["achieved_over_step"] / ceil3
+            if "wide_mlp" in line and "gemm_achieved_tflops" in line["wide_mlp"]:
+                w = line["wide_mlp"]
+                w["frac_of_bf16_sustained"] = w["gemm_achieved_tflops"] / bf16_sus
+                w["frac_of_3xtf32_ceiling"] = w["gemm_achieved_tflops"] / ceil3
+                w["frac_of_3xtf32_ceiling_over_step"] = w["achieved_tflops_over_step_per_gpu"] / ceil3
         except Exception as e:  # keep the bench line even if the auxiliary measurement fails
             line["roofline"] = {"bound": "tensor", "achieved": None, "peak": bf16_sus, "unit": "TFLOP/s",
                                 "frac": None, "traffic": None, "error": str(e)}
+        if peaks:
+            line["measured_peaks_live"] = peaks
         if not args.no_cpu_baseline and world >= 1:
             per, blas, cores = cpu_oracle_time(S, B, hidden, 1)
             n = int(max(1, min(50, args.cpu_seconds / max(per, 1e-3))))
@@ -380,9 +497,11 @@ def main():
         print(json.dumps(line))
     if world > 1 and d.comm_status() != 0:
         raise SystemExit("gradient exchange timed out on a peer: the run is invalid")
+    if parity is not None and not parity["ok"]:
+        raise SystemExit("data-parallel parity check failed: " + json.dumps(parity))
+    torch.cuda.synchronize()
     if dist is not None:
-        torch.cuda.synchronize()
-        dist.barrier()
+        dist.barrier(group=cpu_group)       # the other ranks wait on the host while rank 0 runs the CPU leg
     d.close()
     if dist is not None:
         dist.destroy_process_group()

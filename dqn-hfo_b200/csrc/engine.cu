@@ -232,7 +232,7 @@ struct SplitMat {           // [2][rows][ld] fp32 in HBM
 
 struct Op {                 // one kernel launch of the update / act sequence
   enum Kind { GEMM, GEMM_GROUP_UNUSED, GATHER, SAMPLE, HEAD_FWD, CRITIC_HEAD, ACTOR_HEAD_BWD, HEAD_BWD_W, COLSUM, REDUCE,
-              ALLREDUCE, P2P_ALLREDUCE, ADAM, PREP, FINALIZE, FORK, JOIN } kind;
+              ALLREDUCE, P2P_ALLREDUCE, ADAM, PREP, FINALIZE, FORK, JOIN, ACT_STAGE, ACT_LAYER } kind;
   int branch = 0;           // 0 = main stream; 1, 2 = side streams between FORK and JOIN
   int wait_ev = -1;         // event the op's stream waits for before the launch (cross-branch edge)
   int rec_ev = -1;          // event recorded on the op's stream after the launch
@@ -240,7 +240,7 @@ struct Op {                 // one kernel launch of the update / act sequence
   int variant = 0;          // 0: always; 1: only when indices are drawn on the device; 2: only when injected
   GemmArgs gemm; dim3 grid;
   GatherArgs gather; HeadArgs head; CriticHeadArgs ch; ActorHeadBwdArgs ahb; HeadBwdWArgs hbw; ColsumArgs cs;
-  ReduceArgs red; AdamArgs adam; P2PArgs p2p;
+  ReduceArgs red; AdamArgs adam; P2PArgs p2p; ActStageArgs ast; ActLayerArgs al;
   float *ar_buf = nullptr; size_t ar_count = 0;
   int blocks = 0;
 };
@@ -270,7 +270,8 @@ struct dqnb_handle_s {
   float *Gr[2] = {nullptr, nullptr};  // gradient the optimiser consumes: G, or the all-reduced copy (P2P exchange)
   float *xchg = nullptr; long long xchg_floats = 0;   // IPC-exportable exchange allocation (world_size > 1)
   long long x_in[2] = {0, 0}, x_out[2] = {0, 0}, x_flag = 0;
-  P2PTable *p2p_tab = nullptr; unsigned int *p2p_epoch = nullptr, *p2p_ticket = nullptr; int *p2p_err = nullptr;
+  P2PTable *p2p_tab = nullptr; unsigned int *p2p_epoch = nullptr, *p2p_ticket = nullptr;
+  int *p2p_err = nullptr; volatile int *h_p2p_err = nullptr;   // sticky exchange-failure flag: host-mapped pinned word
   float *p2p_block_ss = nullptr;
   std::vector<void *> ipc_opened;
   int comm_mode = 0;                  // 0 none, 1 NCCL all-reduce, 2 P2P exchange kernel
@@ -295,6 +296,17 @@ struct dqnb_handle_s {
   SplitMat Xact, Xeval, actE[DQNB_MAX_HIDDEN];
   float *out16_act = nullptr;
   float *h_act_in = nullptr, *h_act_out = nullptr;   // pinned staging
+  // skinny act path (kernels.cuh act_*): own stream + graph, fp32 actor snapshots, host-mapped I/O
+  cudaStream_t astream = nullptr;
+  cudaGraphExec_t act_graph = nullptr;
+  float *snapA = nullptr;                       // [2][gA.flat]
+  unsigned int *act_cur = nullptr, *act_sel = nullptr;
+  ActCtl *h_ctl = nullptr, *d_ctl = nullptr;    // mapped pinned
+  float *h_ax = nullptr, *d_ax = nullptr;       // pinned call block {n, seq, -, - | rows [kActMaxRows][Sp]} and its device copy
+  float *h_ay = nullptr, *d_ay = nullptr;       // mapped pinned rows out [kActMaxRows][16]
+  float *actY[2] = {nullptr, nullptr};
+  unsigned int act_seq = 0; int act_rows_pending = 0; bool act_skinny_pending = false;
+  int act_kernels = 0;
   // step state / results
   StepState *st = nullptr;
   float *results = nullptr; int max_slots = 4096;
@@ -313,10 +325,20 @@ struct dqnb_handle_s {
   cudaEvent_t ev_copy = nullptr, ev_gather = nullptr;
   bool copy_pending = false;          // the compute stream has not yet been ordered after the last append
   volatile unsigned long long *h_done = nullptr; unsigned long long *d_done = nullptr;   // mapped: last finished update
-  // op lists + graphs
-  std::vector<Op> update_ops, act_ops, eval_ops;
-  cudaGraphExec_t graph_sampled = nullptr, graph_injected = nullptr;
-  int kernels_per_update_sampled = 0, kernels_per_update_injected = 0;
+  // The minibatch inputs (gather outputs) exist twice: update t reads set t % 2 while the gather of update t + 1
+  // fills the other one on the gather stream, beside the running update (the fields above are the set the op list
+  // being built refers to).
+  struct InputSet { SplitMat Xs, Xsn, Xc, Xct, Xcp; float *reward = nullptr, *mc = nullptr, *term = nullptr; int32_t *idx = nullptr; };
+  InputSet in[2];
+  cudaStream_t gstream = nullptr;                      // gathers (the only reader of the replay ring)
+  cudaEvent_t ev_set_ready[2] = {nullptr, nullptr};    // gather into set s finished
+  cudaEvent_t ev_set_free[2] = {nullptr, nullptr};     // the last update that read set s finished
+  int last_set = 0;                                    // set of the most recent update (debug taps, peeks)
+  // op lists + graphs (one per input set)
+  std::vector<Op> update_ops_set[2], act_ops, eval_ops;
+  std::vector<Op> &update_ops = update_ops_set[0];
+  cudaGraphExec_t graph[2] = {nullptr, nullptr};
+  int kernels_per_update = 0;
   int64_t launches = 0;
   void *comm = nullptr;
   long long *trace = nullptr; int trace_ops = 0;   // DQNB_TRACE=1: per-GEMM timeline stamps (gemm.cuh DQNB_STAMP)
@@ -362,6 +384,9 @@ struct Tuning {
   int sched;        // 0: three forward chains at once; 1: (target actor || critic) then (target critic || actor)
   int fuse_colsum;  // 1: bias gradients of the layers below the top one come from the dX epilogues (0: colsum launches)
   int fuse_tl;      // 1: TD target + critic loss head in one launch
+  int gather_ahead; // 1: gathers run on a stream of their own into the idle input set, beside the previous update
+  int actor_late;   // 1: the actor's forward on s (consumed only by the policy pass) starts with the critic's backward
+                    //    pass instead of beside the target critic, which then runs alone with cluster split-K
   int cluster_b;    // 1: cluster split-K also for the target chains, which share the machine with the side chains
   int pdl_early;    // GEMM kernels: 1 = launch_dependents right after the wait, 0 = after the last MMA issue
   int bn_big;       // 128: dX / dW GEMMs that fill the machine with 128x64 tiles anyway use 128x128 tiles (half the CTAs,
@@ -372,13 +397,15 @@ struct Tuning {
     sched = env_int("DQNB_SCHED", 1);
     fuse_colsum = env_int("DQNB_FUSE_COLSUM", 1);
     fuse_tl = env_int("DQNB_FUSE_TL", 1);
+    gather_ahead = env_int("DQNB_GATHER_AHEAD", 1);
+    actor_late = env_int("DQNB_ACTOR_LATE", 0);
     cluster_b = env_int("DQNB_CLUSTER_B", 0);
     pdl_early = env_int("DQNB_PDL_EARLY", 0);
     bn_big = env_int("DQNB_BN_BIG", 64);
     bn_fwd = env_int("DQNB_BN_FWD", 64);
     bn_fwd_side = env_int("DQNB_BN_FWD_SIDE", 64);
     bn_dx = env_int("DQNB_BN_DX", 64);
-    bn_dw = env_int("DQNB_BN_DW", 64);
+    bn_dw = env_int("DQNB_BN_DW", 128);   // 128-wide tiles, twice the splits: half the mainloop per CTA in the tail of a pass
     st_fwd = env_int("DQNB_ST_FWD", 0);
     st_fwd_side = env_int("DQNB_ST_FWD_SIDE", 0);
     st_dx = env_int("DQNB_ST_DX", 0);
@@ -553,10 +580,7 @@ static int launch_op(dqnb_handle_s *h, const Op &op, cudaStream_t s) {
       break;
     case Op::GEMM_GROUP_UNUSED: break;
     case Op::GATHER: e = launch_k(gather_kernel, dim3(h->Bp), dim3(128), 0, s, op.gather); break;
-    case Op::SAMPLE:
-      e = launch_k(sample_kernel, dim3((h->B + 255) / 256), dim3(256), 0, s, (const StepState *)h->st,
-                   (unsigned long long)h->cfg.seed, h->B, h->idx);
-      break;
+    case Op::SAMPLE: break;
     case Op::HEAD_FWD: e = launch_k(head_fwd_kernel, dim3(op.blocks), dim3(256), 0, s, op.head); break;
     case Op::CRITIC_HEAD: e = launch_k(critic_head_kernel, dim3(op.blocks), dim3(256), 0, s, op.ch); break;
     case Op::ACTOR_HEAD_BWD: e = launch_k(actor_head_bwd_kernel, dim3(op.blocks), dim3(256), 0, s, op.ahb); break;
@@ -565,11 +589,11 @@ static int launch_op(dqnb_handle_s *h, const Op &op, cudaStream_t s) {
     case Op::REDUCE: e = launch_k(reduce_kernel, dim3(op.blocks), dim3(256), 0, s, op.red); break;
     case Op::P2P_ALLREDUCE: e = launch_k(p2p_allreduce_kernel, dim3(op.blocks), dim3(512), 0, s, op.p2p); break;
     case Op::ADAM: e = launch_k(adam_kernel, dim3(op.blocks), dim3(256), 0, s, op.adam); break;
-    case Op::PREP: e = launch_k(prep_kernel, dim3(1), dim3(32), 0, s, h->st, h->hp); break;
+    case Op::PREP:
     case Op::FINALIZE:
-      e = launch_k(finalize_kernel, dim3(1), dim3(32), 0, s, h->st, (const float *)(h->G[1] + h->gC.flat),
-                   (const float *)(h->G[0] + h->gA.flat), h->results, h->max_slots);
-      break;
+      return 0;
+    case Op::ACT_STAGE: e = launch_k(act_stage_kernel, dim3(1), dim3(32), 0, s, op.ast); break;
+    case Op::ACT_LAYER: e = launch_k(act_layer_kernel, dim3(op.blocks), dim3(op.al.last ? 512 : 256), 0, s, op.al); break;
     case Op::FORK:
     case Op::JOIN:
       return 0;   // stream plumbing, handled by run_ops
@@ -587,7 +611,6 @@ static int launch_op(dqnb_handle_s *h, const Op &op, cudaStream_t s) {
 static int run_ops(dqnb_handle_s *h, const std::vector<Op> &ops, cudaStream_t s, bool skip_sample, int *count) {
   int n = 0;
   for (const Op &op : ops) {
-    if (op.variant == (skip_sample ? 1 : 2)) continue;
     if (op.kind == Op::GATHER) continue;       // launched by enqueue_update ahead of the graph
     if (op.kind == Op::FORK) {          // side streams pick up after everything queued on the main one
       DQNB_CUDA(cudaEventRecord(h->ev_fork, s));
@@ -661,7 +684,7 @@ static Op make_colsum(dqnb_handle_s *h, const NetGeom &g, int l0, int l1) {
 // layer, whose dZ comes from a head kernel, keeps a colsum launch (behind its weight gradient).
 static int build_backward(dqnb_handle_s *h, const NetGeom &g, const float *P, const SplitMat &X,
                           SplitMat *acts, bool want_dw, SegTable *segs, const Op *head_bwd_w,
-                          std::vector<Op> &ops) {
+                          std::vector<Op> &ops, int extra_join_mask = 0) {
   const int top = g.n_hidden - 1;
   if (g.n_hidden + 1 > 8) DQNB_FAIL("too many layers for the event table");
   const bool fuse_cs = want_dw && h->cfg.gemm_mode == DQNB_GEMM_TCGEN05_3XTF32 && tuning().fuse_colsum;
@@ -710,7 +733,7 @@ static int build_backward(dqnb_handle_s *h, const NetGeom &g, const float *P, co
     T.begin[hs] = g.hw_off; T.end[hs] = g.flat; T.nsplit[hs] = kGradSplits;   // head W, b (+ zero tail)
     T.src[hs] = h->Gpart[g.critic] + g.hw_off; T.stride[hs] = h->gpart_stride[g.critic];
     T.n = hs + 1;
-    Op j; j.kind = Op::JOIN; j.mask = fork_mask; ops.push_back(j);
+    Op j; j.kind = Op::JOIN; j.mask = fork_mask | extra_join_mask; ops.push_back(j);
   }
   return 0;
 }
@@ -737,6 +760,7 @@ static void build_solver(dqnb_handle_s *h, int is_critic, const SegTable &segs, 
       x.tab = h->p2p_tab; x.world = h->cfg.world_size; x.rank = h->cfg.rank; x.net = is_critic;
       x.in_off = h->x_in[is_critic]; x.out_off = h->x_out[is_critic]; x.flag_off = h->x_flag;
       x.count = g.flat + 4; x.epoch = h->p2p_epoch; x.ticket = h->p2p_ticket; x.err = h->p2p_err;
+      x.timeout_ns = (unsigned long long)std::max(1, env_int("DQNB_P2P_TIMEOUT_MS", 20000)) * 1000000ull;
       x.block_ss = h->p2p_block_ss;
       ar.blocks = 128;
       ops.push_back(ar);            // also delivers every rank's share of ||g||^2: no separate norm pass
@@ -760,6 +784,7 @@ static void build_solver(dqnb_handle_s *h, int is_critic, const SegTable &segs, 
   d.P = h->P[is_critic ? DQNB_CRITIC : DQNB_ACTOR]; d.p_plane = g.flat;
   d.T = h->P[is_critic ? DQNB_CRITIC_TARGET : DQNB_ACTOR_TARGET]; d.t_plane = g.flat;
   d.st = h->st; d.st_out = h->st; d.is_critic = is_critic; d.hp = h->hp;
+  d.comm_err = (multi && h->comm_mode == 2) ? h->p2p_err : nullptr;
   ad.blocks = blocks;
   ops.push_back(ad);
 }
@@ -792,8 +817,15 @@ static Op make_head_bwd_w(dqnb_handle_s *h, const NetGeom &g, const float *d16, 
   return w;
 }
 
-static int build_update_ops(dqnb_handle_s *h) {
-  std::vector<Op> &ops = h->update_ops;
+static void select_input_set(dqnb_handle_s *h, int set) {
+  const dqnb_handle_s::InputSet &I = h->in[set];
+  h->Xs = I.Xs; h->Xsn = I.Xsn; h->Xc = I.Xc; h->Xct = I.Xct; h->Xcp = I.Xcp;
+  h->reward = I.reward; h->mc = I.mc; h->term = I.term; h->idx = I.idx;
+}
+
+static int build_update_ops_for(dqnb_handle_s *h, int set) {
+  select_input_set(h, set);
+  std::vector<Op> &ops = h->update_ops_set[set];
   ops.clear();
   const NetGeom &gA = h->gA, &gC = h->gC;
   float *PA = h->P[DQNB_ACTOR], *PC = h->P[DQNB_CRITIC], *PAT = h->P[DQNB_ACTOR_TARGET], *PCT = h->P[DQNB_CRITIC_TARGET];
@@ -845,11 +877,13 @@ static int build_update_ops(dqnb_handle_s *h) {
   op.branch = 0;
   if (build_forward(h, gA, PAT, h->Xsn, h->actAT, ops, true, tuning().cluster_b != 0)) return -1;
   op_head_fwd(gA, PAT, h->actAT[topA], h->B, h->a16_t, &h->Xct, h->S, &op);
-  if (sched == 1) op.rec_ev = kEvActorStart;
+  const bool actor_late = sched == 1 && tuning().actor_late;
+  constexpr int kLateBranch = 8;                  // a side stream nothing else uses
+  if (sched == 1 && !actor_late) op.rec_ev = kEvActorStart;
   ops.push_back(op);
   op.rec_ev = -1;
-  if (sched == 1 && push_actor_chain(2, kEvActorStart)) return -1;
-  if (build_forward(h, gC, PCT, h->Xct, h->actCT, ops, true, tuning().cluster_b != 0)) return -1;
+  if (sched == 1 && !actor_late && push_actor_chain(2, kEvActorStart)) return -1;
+  if (build_forward(h, gC, PCT, h->Xct, h->actCT, ops, true, tuning().cluster_b != 0 || actor_late)) return -1;
   if (tuning().fuse_tl) {
     // dqn.cpp:892-900 TD target and the head of critic_solver_->Step(1) (loss + head backward) in one launch
     op.kind = Op::JOIN; op.mask = fork_mask; ops.push_back(op);
@@ -863,8 +897,12 @@ static int build_update_ops(dqnb_handle_s *h) {
     // rest of critic_solver_->Step(1): loss, backward, clip, Adam (+ soft update of the target critic)
     push_critic_head(h, QMODE_LOSS, PC, h->actC[topC], h->q, ops);
   }
+  if (actor_late) {
+    ops.back().rec_ev = kEvActorStart;            // the critic's loss head is done: the backward pass starts
+    if (push_actor_chain(kLateBranch, kEvActorStart)) return -1;
+  }
   Op hbw = make_head_bwd_w(h, gC, h->d16c, h->actC[topC]);
-  if (build_backward(h, gC, PC, h->Xc, h->actC, true, &h->segs[1], &hbw, ops)) return -1;
+  if (build_backward(h, gC, PC, h->Xc, h->actC, true, &h->segs[1], &hbw, ops, actor_late ? 1 << (kLateBranch - 1) : 0)) return -1;
   build_solver(h, 1, h->segs[1], 0.5f * h->hp.inv_batch_global, ops);
   // dqn.cpp:913-916 critic forward on (s, a_pi) with the updated critic
   if (build_forward(h, gC, PC, h->Xcp, h->actC, ops)) return -1;
@@ -895,15 +933,24 @@ static int build_update_ops(dqnb_handle_s *h) {
     AdamArgs &d = ops.back().adam;
     d.finalize = 1; d.ticket = h->ticket; d.g_critic_tail = h->Gr[1] + gC.flat; d.g_actor_tail = h->Gr[0] + gA.flat;
     d.results = h->results; d.max_slots = h->max_slots; d.done = h->d_done;
+    d.snap = h->snapA; d.snap_stride = gA.flat; d.act_cur = h->act_cur;
   }
+  for (Op &o : ops)     // the critic's reduction (first optimiser kernel) refreshes the per-update Adam scalars
+    if (o.kind == Op::REDUCE && o.red.do_reduce) { o.red.do_prep = 1; o.red.st = h->st; o.red.hp = h->hp; break; }
+  return 0;
+}
+static int build_update_ops(dqnb_handle_s *h) {
+  for (int set = 1; set >= 0; --set)
+    if (build_update_ops_for(h, set)) return -1;
   return 0;
 }
 
 // DQNB_TRACE=1: every op of the update sequence gets a kTraceSlots-slot timeline record (kernels.cuh trace_begin/end)
 static void attach_trace(dqnb_handle_s *h) {
   if (!h->trace) return;
-  for (int i = 0; i < (int)h->update_ops.size() && i < h->trace_ops; ++i) {
-    Op &op = h->update_ops[i];
+  for (int set = 0; set < 2; ++set)
+  for (int i = 0; i < (int)h->update_ops_set[set].size() && i < h->trace_ops; ++i) {
+    Op &op = h->update_ops_set[set][i];
     long long *t = h->trace + kTraceSlots * i;
     switch (op.kind) {
       case Op::GEMM: op.gemm.p.dbg_clk = t; break;
@@ -918,6 +965,34 @@ static void attach_trace(dqnb_handle_s *h) {
       case Op::P2P_ALLREDUCE: op.p2p.trace = t; break;
       default: break;
     }
+  }
+}
+
+// SelectActionGreedily for up to kActMaxRows states: stage + one launch per layer + head, on the act stream
+static void build_skinny_act_ops(dqnb_handle_s *h, std::vector<Op> &ops) {
+  const NetGeom &g = h->gA;
+  ops.clear();
+  Op op;
+  op.kind = Op::ACT_STAGE;
+  memset(&op.ast, 0, sizeof(op.ast));
+  op.ast.cur = h->act_cur; op.ast.sel = h->act_sel;
+  ops.push_back(op);
+  const float *x = h->d_ax + kActHdr;
+  int ldx = h->Sp;
+  for (int l = 0; l <= g.n_hidden; ++l) {
+    const bool head = l == g.n_hidden;
+    Op o;
+    o.kind = Op::ACT_LAYER;
+    ActLayerArgs &a = o.al;
+    memset(&a, 0, sizeof(a));
+    a.ctl = h->d_ctl; a.hdr = reinterpret_cast<const int *>(h->d_ax); a.snap = h->snapA; a.snap_stride = g.flat; a.sel = h->act_sel;
+    a.w_off = head ? g.hw_off : g.L[l].w_off; a.b_off = head ? g.hb_off : g.L[l].b_off;
+    a.Kp = head ? g.Hp : g.L[l].Kp; a.N = head ? g.head_real : g.L[l].Np;
+    a.X = x; a.ldx = ldx; a.Y = h->actY[l & 1]; a.ldy = head ? 16 : g.L[l].Np;
+    a.lrelu = head ? 0 : 1; a.last = head ? 1 : 0; a.h_out = h->d_ay;
+    o.blocks = head ? 1 : (a.N + 7) / 8;
+    ops.push_back(o);
+    x = a.Y; ldx = a.ldy;
   }
 }
 
@@ -963,8 +1038,10 @@ int dqnb_destroy(dqnb_handle h) {
   if (!h) return 0;
   cudaSetDevice(h->cfg.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  if (h->graph_sampled) cudaGraphExecDestroy(h->graph_sampled);
-  if (h->graph_injected) cudaGraphExecDestroy(h->graph_injected);
+  if (h->gstream) cudaStreamSynchronize(h->gstream);
+  if (h->astream) cudaStreamSynchronize(h->astream);
+  if (h->act_graph) cudaGraphExecDestroy(h->act_graph);
+  for (int i = 0; i < 2; ++i) if (h->graph[i]) cudaGraphExecDestroy(h->graph[i]);
   if (h->comm && nccl().CommDestroy) nccl().CommDestroy(h->comm);
   for (void *p : h->ipc_opened) cudaIpcCloseMemHandle(p);
   for (void *p : h->allocs) cudaFree(p);
@@ -981,6 +1058,12 @@ int dqnb_destroy(dqnb_handle h) {
   for (int i = 0; i < dqnb_handle_s::kStageSlots; ++i) if (h->ev_stage[i]) cudaEventDestroy(h->ev_stage[i]);
   if (h->ev_copy) cudaEventDestroy(h->ev_copy);
   if (h->ev_gather) cudaEventDestroy(h->ev_gather);
+  for (int i = 0; i < 2; ++i) {
+    if (h->ev_set_ready[i]) cudaEventDestroy(h->ev_set_ready[i]);
+    if (h->ev_set_free[i]) cudaEventDestroy(h->ev_set_free[i]);
+  }
+  if (h->gstream) cudaStreamDestroy(h->gstream);
+  if (h->astream) cudaStreamDestroy(h->astream);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return 0;
@@ -1011,6 +1094,11 @@ static int create_impl(const dqnb_config *cfg, dqnb_handle_s *h) {
   DQNB_CUDA(cudaEventCreate(&h->ev0));
   DQNB_CUDA(cudaEventCreate(&h->ev1));
   DQNB_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  if (tuning().gather_ahead) DQNB_CUDA(cudaStreamCreateWithPriority(&h->gstream, cudaStreamNonBlocking, prio_lo));
+  for (int i = 0; i < 2; ++i) {
+    DQNB_CUDA(cudaEventCreateWithFlags(&h->ev_set_ready[i], cudaEventDisableTiming));
+    DQNB_CUDA(cudaEventCreateWithFlags(&h->ev_set_free[i], cudaEventDisableTiming));
+  }
   for (int i = 0; i < dqnb_handle_s::kStageSlots; ++i) DQNB_CUDA(cudaEventCreateWithFlags(&h->ev_stage[i], cudaEventDisableTiming));
   DQNB_CUDA(cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming));
   DQNB_CUDA(cudaEventCreateWithFlags(&h->ev_gather, cudaEventDisableTiming));
@@ -1044,8 +1132,16 @@ static int create_impl(const dqnb_config *cfg, dqnb_handle_s *h) {
     h->xchg_floats = h->x_flag + 256;
     if (dalloc(h, &h->xchg, (size_t)h->xchg_floats)) return -1;
     for (int n = 0; n < 2; ++n) { h->G[n] = h->xchg + h->x_in[n]; h->Gr[n] = h->G[n]; }
-    if (dalloc(h, &h->p2p_tab, 1) || dalloc(h, &h->p2p_epoch, 2) || dalloc(h, &h->p2p_ticket, 2) || dalloc(h, &h->p2p_err, 1) ||
+    if (dalloc(h, &h->p2p_tab, 1) || dalloc(h, &h->p2p_epoch, 2) || dalloc(h, &h->p2p_ticket, 2) ||
         dalloc(h, &h->p2p_block_ss, 2 * 256)) return -1;
+    {
+      void *hp = nullptr, *dp = nullptr;
+      DQNB_CUDA(cudaHostAlloc(&hp, 64, cudaHostAllocMapped));
+      memset(hp, 0, 64);
+      h->pinned.push_back(hp);
+      DQNB_CUDA(cudaHostGetDevicePointer(&dp, hp, 0));
+      h->h_p2p_err = (volatile int *)hp; h->p2p_err = (int *)dp;
+    }
   } else {
     if (dalloc(h, &h->G[0], fA + 4) || dalloc(h, &h->G[1], fC + 4)) return -1;
     h->Gr[0] = h->G[0]; h->Gr[1] = h->G[1];
@@ -1063,10 +1159,15 @@ static int create_impl(const dqnb_config *cfg, dqnb_handle_s *h) {
   const size_t cap = (size_t)c.replay_capacity;
   h->rw = 2 * h->Sp + kMiscStride;
   if (dalloc(h, &h->ring, cap * h->rw)) return -1;
-  if (dalloc(h, &h->idx, (size_t)h->Bp)) return -1;
-  if (alloc_mat(h, &h->Xs, h->Bp, h->Sp) || alloc_mat(h, &h->Xsn, h->Bp, h->Sp) || alloc_mat(h, &h->Xc, h->Bp, h->Kc) ||
-      alloc_mat(h, &h->Xct, h->Bp, h->Kc) || alloc_mat(h, &h->Xcp, h->Bp, h->Kc)) return -1;
-  float **vecs[] = {&h->reward, &h->mc, &h->term, &h->y, &h->q_next, &h->q, &h->q_pi};
+  for (int set = 0; set < 2; ++set) {
+    dqnb_handle_s::InputSet &I = h->in[set];
+    if (dalloc(h, &I.idx, (size_t)h->Bp)) return -1;
+    if (alloc_mat(h, &I.Xs, h->Bp, h->Sp) || alloc_mat(h, &I.Xsn, h->Bp, h->Sp) || alloc_mat(h, &I.Xc, h->Bp, h->Kc) ||
+        alloc_mat(h, &I.Xct, h->Bp, h->Kc) || alloc_mat(h, &I.Xcp, h->Bp, h->Kc)) return -1;
+    if (dalloc(h, &I.reward, (size_t)h->Bp) || dalloc(h, &I.mc, (size_t)h->Bp) || dalloc(h, &I.term, (size_t)h->Bp)) return -1;
+  }
+  select_input_set(h, 0);
+  float **vecs[] = {&h->y, &h->q_next, &h->q, &h->q_pi};
   for (float **v : vecs) if (dalloc(h, v, (size_t)h->Bp)) return -1;
   const int rows16 = std::max(h->Bp, h->An);
   float **m16[] = {&h->a16_t, &h->a16_pi, &h->d16c, &h->d16a, &h->out16_act};
@@ -1079,6 +1180,25 @@ static int create_impl(const dqnb_config *cfg, dqnb_handle_s *h) {
   }
   if (alloc_mat(h, &h->Xact, h->An, h->Sp) || alloc_mat(h, &h->Xeval, h->An, h->Kc)) return -1;
   if (halloc(h, &h->h_act_in, (size_t)2 * h->An * h->Kc) || halloc(h, &h->h_act_out, (size_t)h->An * 16)) return -1;
+  {   // skinny act path: snapshots, staging, host-mapped control / rows
+    int maxNp = h->Sp;
+    for (int l = 0; l < c.n_hidden; ++l) maxNp = std::max(maxNp, h->gA.L[l].Np);
+    if (dalloc(h, &h->snapA, (size_t)2 * fA) || dalloc(h, &h->act_cur, 1) || dalloc(h, &h->act_sel, 1) ||
+        dalloc(h, &h->d_ax, (size_t)kActHdr + (size_t)kActMaxRows * h->Sp) || dalloc(h, &h->actY[0], (size_t)kActMaxRows * maxNp) ||
+        dalloc(h, &h->actY[1], (size_t)kActMaxRows * maxNp)) return -1;
+    auto mapped = [&](size_t bytes, void **hp, void **dp) -> int {
+      DQNB_CUDA(cudaHostAlloc(hp, bytes, cudaHostAllocMapped));
+      memset(*hp, 0, bytes);
+      h->pinned.push_back(*hp);
+      DQNB_CUDA(cudaHostGetDevicePointer(dp, *hp, 0));
+      return 0;
+    };
+    if (mapped(sizeof(ActCtl), (void **)&h->h_ctl, (void **)&h->d_ctl) ||
+        mapped(sizeof(float) * kActMaxRows * 16, (void **)&h->h_ay, (void **)&h->d_ay)) return -1;
+    if (halloc(h, &h->h_ax, (size_t)kActHdr + (size_t)kActMaxRows * h->Sp)) return -1;
+    if (h->gA.head_real > 16) DQNB_FAIL("act path: head wider than 16");
+    DQNB_CUDA(cudaStreamCreateWithPriority(&h->astream, cudaStreamNonBlocking, prio_hi));
+  }
   if (dalloc(h, &h->st, 1) || dalloc(h, &h->ticket, 1)) return -1;
   {   // results live in mapped pinned host memory: reading them back needs a stream sync, no copy
     void *hp = nullptr, *dp = nullptr;
@@ -1140,6 +1260,13 @@ int dqnb_set_params(dqnb_handle h, int net, const float *params) {
   DQNB_CUDA(cudaMemcpyAsync(tmp, in.data(), sizeof(float) * g.flat, cudaMemcpyHostToDevice, h->stream));
   split_kernel<<<(unsigned)((g.flat + 255) / 256), 256, 0, h->stream>>>(tmp, h->P[net], h->P[net] + g.flat, g.flat);
   DQNB_CUDA(cudaGetLastError());
+  if (net == DQNB_ACTOR) {
+    // the act path reads fp32 snapshots of the actor: both buffers take the new weights (no act call is in flight
+    // on the caller's side while it replaces the weights: same single-threaded contract as the reference)
+    DQNB_CUDA(cudaStreamSynchronize(h->astream));
+    DQNB_CUDA(cudaMemcpyAsync(h->snapA, tmp, sizeof(float) * g.flat, cudaMemcpyDeviceToDevice, h->stream));
+    DQNB_CUDA(cudaMemcpyAsync(h->snapA + g.flat, tmp, sizeof(float) * g.flat, cudaMemcpyDeviceToDevice, h->stream));
+  }
   DQNB_CUDA(cudaStreamSynchronize(h->stream));
   DQNB_CUDA(cudaFree(tmp));
   return 0;
@@ -1261,6 +1388,7 @@ static int order_compute_after_copies(dqnb_handle h) {
 }
 static int sync_all(dqnb_handle h) {
   DQNB_CUDA(cudaStreamSynchronize(h->copy_stream));
+  if (h->gstream) DQNB_CUDA(cudaStreamSynchronize(h->gstream));
   DQNB_CUDA(cudaStreamSynchronize(h->stream));
   return 0;
 }
@@ -1372,50 +1500,76 @@ int dqnb_get_transitions(dqnb_handle h, int32_t first, int32_t n, float *s, floa
 }
 
 // ----------------------------------- update ----------------------------------------------------
-static int ensure_graph(dqnb_handle h, bool injected) {
-  cudaGraphExec_t *slot = injected ? &h->graph_injected : &h->graph_sampled;
+static int ensure_graph(dqnb_handle h, int set) {
+  cudaGraphExec_t *slot = &h->graph[set];
   if (*slot) return 0;
   cudaGraph_t graph = nullptr;
   int count = 0;
   DQNB_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-  int rc = run_ops(h, h->update_ops, h->stream, injected, &count);
+  int rc = run_ops(h, h->update_ops_set[set], h->stream, false, &count);
   cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
   if (rc) { if (graph) cudaGraphDestroy(graph); return -1; }
   DQNB_CUDA(e);
   DQNB_CUDA(cudaGraphInstantiate(slot, graph, 0));
   DQNB_CUDA(cudaGraphDestroy(graph));
-  (injected ? h->kernels_per_update_injected : h->kernels_per_update_sampled) = count;
+  h->kernels_per_update = count;
   return 0;
 }
 
-static int enqueue_update(dqnb_handle h, bool injected) {
-  h->host_step += 1;
+// One update = the gather (dqn.cpp:846-887), the one reader of the replay ring, then the captured graph.  The gather of
+// update t fills input set t % 2 on the gather stream: it waits for the appends queued so far (ev_copy) and for the
+// last update that read this set (t - 2), not for update t - 1, so it runs beside it; an event tells the copy stream
+// "ring consumed" (append_rows).  Injected indices travel on the same stream ahead of the gather.
+static int enqueue_update(dqnb_handle h, const int32_t *injected_idx) {
+  const int set = (int)(h->host_step & 1ull);
+  cudaStream_t gs = h->gstream ? h->gstream : h->stream;
   if (h->trace) DQNB_CUDA(cudaMemsetAsync(h->trace, 0xFF, sizeof(long long) * kTraceSlots * h->trace_ops, h->stream));
-  // The gather (dqn.cpp:846-887) is the one reader of the replay ring: it runs ahead of the captured graph so that
-  // an event can mark "ring consumed" for the copy stream (append_rows).
-  if (order_compute_after_copies(h)) return -1;
-  for (const Op &op : h->update_ops)
-    if (op.kind == Op::GATHER && op.variant == (injected ? 2 : 1)) {
-      if (launch_op(h, op, h->stream)) return -1;
+  if (h->gstream) {
+    DQNB_CUDA(cudaStreamWaitEvent(gs, h->ev_copy, 0));
+    DQNB_CUDA(cudaStreamWaitEvent(gs, h->ev_set_free[set], 0));
+    h->copy_pending = false;
+  } else if (order_compute_after_copies(h)) {
+    return -1;
+  }
+  if (injected_idx) DQNB_CUDA(cudaMemcpyAsync(h->in[set].idx, injected_idx, sizeof(int32_t) * h->B, cudaMemcpyHostToDevice, gs));
+  for (const Op &op : h->update_ops_set[set])
+    if (op.kind == Op::GATHER && op.variant == (injected_idx ? 2 : 1)) {
+      Op g = op;
+      g.gather.step = h->host_step;          // == StepState::step when this update runs
+      if (launch_op(h, g, gs)) return -1;
       h->launches += 1;
     }
-  DQNB_CUDA(cudaEventRecord(h->ev_gather, h->stream));
+  DQNB_CUDA(cudaEventRecord(h->ev_gather, gs));
+  if (h->gstream) {
+    DQNB_CUDA(cudaEventRecord(h->ev_set_ready[set], gs));
+    DQNB_CUDA(cudaStreamWaitEvent(h->stream, h->ev_set_ready[set], 0));
+  }
   if (h->cfg.use_graph) {
-    if (ensure_graph(h, injected)) return -1;
-    DQNB_CUDA(cudaGraphLaunch(injected ? h->graph_injected : h->graph_sampled, h->stream));
-    h->launches += injected ? h->kernels_per_update_injected : h->kernels_per_update_sampled;
+    if (ensure_graph(h, set)) return -1;
+    DQNB_CUDA(cudaGraphLaunch(h->graph[set], h->stream));
+    h->launches += h->kernels_per_update;
   } else {
     int count = 0;
-    if (run_ops(h, h->update_ops, h->stream, injected, &count)) return -1;
+    if (run_ops(h, h->update_ops_set[set], h->stream, false, &count)) return -1;
     h->launches += count;
   }
+  if (h->gstream) DQNB_CUDA(cudaEventRecord(h->ev_set_free[set], h->stream));
+  h->last_set = set;
+  h->host_step += 1;
   return 0;
 }
 
 // (critic_loss, avg_q) of the last n updates: the optimiser launch of update k wrote slot k % max_slots of
 // the mapped pinned ring; a stream sync makes them visible
+static int comm_failed(dqnb_handle h) {
+  if (h->h_p2p_err && *h->h_p2p_err != 0)
+    DQNB_FAIL("gradient exchange failed: a peer did not arrive within DQNB_P2P_TIMEOUT_MS; the replicas have stopped updating "
+              "(parameters, Adam moments and iteration counters are those of the last good update)");
+  return 0;
+}
 static int fetch_results(dqnb_handle h, int n, float *critic_loss, float *avg_q) {
   DQNB_CUDA(cudaStreamSynchronize(h->stream));
+  if (comm_failed(h)) return -1;
   for (int i = 0; i < n; ++i) {
     const int slot = (int)((h->host_step - (unsigned long long)n + i) % (unsigned long long)h->max_slots);
     if (critic_loss) critic_loss[i] = h->h_results[2 * slot];
@@ -1429,7 +1583,7 @@ int dqnb_update_async(dqnb_handle h, int32_t n_updates, int64_t *last_step) {
   if (!h || n_updates < 0) DQNB_FAIL("bad argument");
   if (n_updates > 0 && h->ring_size <= 0) DQNB_FAIL("Update on an empty replay memory");
   DQNB_CUDA(cudaSetDevice(h->cfg.device));
-  for (int i = 0; i < n_updates; ++i) if (enqueue_update(h, false)) return -1;
+  for (int i = 0; i < n_updates; ++i) if (enqueue_update(h, nullptr)) return -1;
   if (last_step) *last_step = (int64_t)h->host_step;
   return 0;
 }
@@ -1453,6 +1607,7 @@ int dqnb_results(dqnb_handle h, int64_t first_step, int32_t n, float *critic_los
     }
   }
   if (*h->h_done < last) DQNB_FAIL("update %llu did not complete (device reports %llu)", last, (unsigned long long)*h->h_done);
+  if (comm_failed(h)) return -1;
   for (int i = 0; i < n; ++i) {
     const int slot = (int)(((unsigned long long)first_step - 1 + i) % (unsigned long long)h->max_slots);
     if (critic_loss) critic_loss[i] = h->h_results[2 * slot];
@@ -1469,7 +1624,7 @@ int dqnb_update(dqnb_handle h, int32_t n_updates, float *critic_loss, float *avg
   int done = 0;
   while (done < n_updates) {
     const int chunk = std::min(n_updates - done, h->max_slots);
-    for (int i = 0; i < chunk; ++i) if (enqueue_update(h, false)) return -1;
+    for (int i = 0; i < chunk; ++i) if (enqueue_update(h, nullptr)) return -1;
     if (fetch_results(h, chunk, critic_loss ? critic_loss + done : nullptr, avg_q ? avg_q + done : nullptr)) return -1;
     done += chunk;
   }
@@ -1481,8 +1636,8 @@ int dqnb_update_with_indices(dqnb_handle h, const int32_t *idx, float *critic_lo
   DQNB_CUDA(cudaSetDevice(h->cfg.device));
   for (int i = 0; i < h->B; ++i)
     if (idx[i] < 0 || idx[i] >= h->ring_size) DQNB_FAIL("index %d out of range [0,%d)", idx[i], h->ring_size);
-  DQNB_CUDA(cudaMemcpyAsync(h->idx, idx, sizeof(int32_t) * h->B, cudaMemcpyHostToDevice, h->stream));
-  if (enqueue_update(h, true)) return -1;
+  if (enqueue_update(h, idx)) return -1;     // idx is consumed by an asynchronous copy: wait before returning
+  if (h->gstream) DQNB_CUDA(cudaStreamSynchronize(h->gstream));
   return fetch_results(h, 1, critic_loss, avg_q);
 }
 
@@ -1490,10 +1645,10 @@ int dqnb_benchmark(dqnb_handle h, int32_t n_updates, float *elapsed_ms) {
   if (!h || n_updates <= 0 || !elapsed_ms) DQNB_FAIL("bad argument");
   if (h->ring_size <= 0) DQNB_FAIL("Benchmark on an empty replay memory");
   DQNB_CUDA(cudaSetDevice(h->cfg.device));
-  if (h->cfg.use_graph && ensure_graph(h, false)) return -1;
-  DQNB_CUDA(cudaStreamSynchronize(h->stream));
+  if (h->cfg.use_graph && (ensure_graph(h, 0) || ensure_graph(h, 1))) return -1;
+  if (sync_all(h)) return -1;
   DQNB_CUDA(cudaEventRecord(h->ev0, h->stream));
-  for (int i = 0; i < n_updates; ++i) if (enqueue_update(h, false)) return -1;
+  for (int i = 0; i < n_updates; ++i) if (enqueue_update(h, nullptr)) return -1;
   DQNB_CUDA(cudaEventRecord(h->ev1, h->stream));
   DQNB_CUDA(cudaEventSynchronize(h->ev1));
   DQNB_CUDA(cudaEventElapsedTime(elapsed_ms, h->ev0, h->ev1));
@@ -1526,9 +1681,11 @@ int dqnb_peek_sample_indices(dqnb_handle h, int32_t *idx) {
   if (!h || !idx) DQNB_FAIL("bad argument");
   DQNB_CUDA(cudaSetDevice(h->cfg.device));
   if (order_compute_after_copies(h)) return -1;
-  sample_kernel<<<(h->B + 255) / 256, 256, 0, h->stream>>>(h->st, h->cfg.seed, h->B, h->idx);
+  if (sync_all(h)) return -1;               // neither input set is in use: borrow the idle one's index buffer
+  int32_t *scratch = h->in[(h->host_step & 1ull) ? 1 : 0].idx;
+  sample_kernel<<<(h->B + 255) / 256, 256, 0, h->stream>>>(h->st, h->cfg.seed, h->host_step, h->B, scratch);
   DQNB_CUDA(cudaGetLastError());
-  DQNB_CUDA(cudaMemcpyAsync(idx, h->idx, sizeof(int32_t) * h->B, cudaMemcpyDeviceToHost, h->stream));
+  DQNB_CUDA(cudaMemcpyAsync(idx, scratch, sizeof(int32_t) * h->B, cudaMemcpyDeviceToHost, h->stream));
   DQNB_CUDA(cudaStreamSynchronize(h->stream));
   return 0;
 }
@@ -1556,10 +1713,62 @@ static int stage_rows_split(dqnb_handle h, int n, const float *src, int src_ld, 
   return 0;
 }
 
+static int ensure_act_graph(dqnb_handle h) {
+  if (h->act_graph) return 0;
+  std::vector<Op> ops;
+  build_skinny_act_ops(h, ops);
+  cudaGraph_t graph = nullptr;
+  int count = 0;
+  DQNB_CUDA(cudaStreamBeginCapture(h->astream, cudaStreamCaptureModeThreadLocal));
+  // the call block {n, seq | rows} travels by DMA: one memcpy node at the head of the graph
+  cudaError_t ec = cudaMemcpyAsync(h->d_ax, h->h_ax, sizeof(float) * ((size_t)kActHdr + (size_t)kActMaxRows * h->Sp), cudaMemcpyHostToDevice, h->astream);
+  int rc = ec == cudaSuccess ? run_ops(h, ops, h->astream, false, &count) : -1;
+  cudaError_t e = cudaStreamEndCapture(h->astream, &graph);
+  if (ec != cudaSuccess) { if (graph) cudaGraphDestroy(graph); DQNB_CUDA(ec); }
+  if (rc) { if (graph) cudaGraphDestroy(graph); return -1; }
+  DQNB_CUDA(e);
+  DQNB_CUDA(cudaGraphInstantiate(&h->act_graph, graph, 0));
+  DQNB_CUDA(cudaGraphDestroy(graph));
+  h->act_kernels = count;
+  return 0;
+}
+
+// waits (spinning on the host-mapped sequence word) for the skinny act call in flight, if any
+static int act_wait_done(dqnb_handle h) {
+  if (!h->act_skinny_pending) return 0;
+  unsigned spins = 0;
+  while (h->h_ctl->done != h->act_seq) {
+    if ((++spins & 0xfff) == 0) {
+      const cudaError_t q = cudaStreamQuery(h->astream);
+      if (q == cudaSuccess) break;
+      if (q != cudaErrorNotReady) DQNB_CUDA(q);
+    }
+  }
+  if (h->h_ctl->done != h->act_seq) DQNB_FAIL("act call %u did not complete (device reports %u)", h->act_seq, h->h_ctl->done);
+  h->act_skinny_pending = false;
+  return 0;
+}
+
 int dqnb_select_actions_async(dqnb_handle h, int32_t n, const float *states) {
   if (!h || !states || n <= 0) DQNB_FAIL("bad argument");
   if (n > h->cfg.max_act_batch) DQNB_FAIL("SelectActions: batch %d > max_act_batch %d (dqn.cpp:699)", n, h->cfg.max_act_batch);
   DQNB_CUDA(cudaSetDevice(h->cfg.device));
+  if (act_wait_done(h)) return -1;
+  h->act_rows_pending = n;
+  if (n <= kActMaxRows && !getenv("DQNB_ACT_GEMM")) {
+    // skinny path: own stream and graph, actor snapshot, host-mapped rows: the learner's stream is never touched
+    const int S = h->S, Sp = h->Sp;
+    float *rows = h->h_ax + kActHdr;
+    for (int i = 0; i < n; ++i) memcpy(rows + (size_t)i * Sp, states + (size_t)i * S, sizeof(float) * S);   // padding stays 0
+    reinterpret_cast<int *>(h->h_ax)[0] = n;
+    reinterpret_cast<unsigned int *>(h->h_ax)[1] = ++h->act_seq;
+    if (ensure_act_graph(h)) return -1;
+    DQNB_CUDA(cudaGraphLaunch(h->act_graph, h->astream));
+    h->launches += h->act_kernels;
+    h->act_skinny_pending = true;
+    return 0;
+  }
+  // large batches: the tcgen05 layer kernels on the learner's stream, after whatever is queued there
   DQNB_CUDA(cudaStreamSynchronize(h->stream));
   if (stage_rows_split(h, n, states, h->S, h->S, nullptr, 0, h->Xact)) return -1;
   int count = 0;
@@ -1571,6 +1780,12 @@ int dqnb_select_actions_async(dqnb_handle h, int32_t n, const float *states) {
 
 int dqnb_select_actions_wait(dqnb_handle h, int32_t n, float *out10) {
   if (!h || !out10 || n <= 0) DQNB_FAIL("bad argument");
+  if (n != h->act_rows_pending) DQNB_FAIL("select_actions_wait: %d rows requested, %d enqueued", n, h->act_rows_pending);
+  if (h->act_skinny_pending) {
+    if (act_wait_done(h)) return -1;
+    for (int i = 0; i < n; ++i) memcpy(out10 + (size_t)i * kActorOut, h->h_ay + (size_t)i * 16, sizeof(float) * kActorOut);
+    return 0;
+  }
   DQNB_CUDA(cudaStreamSynchronize(h->stream));
   for (int i = 0; i < n; ++i) memcpy(out10 + (size_t)i * kActorOut, h->h_act_out + (size_t)i * 16, sizeof(float) * kActorOut);
   return 0;
@@ -1600,11 +1815,10 @@ int dqnb_evaluate(dqnb_handle h, int32_t n, const float *states, const float *ac
 }  // extern "C"
 // choosing how gradients are exchanged changes the kernel sequence: rebuild it and drop captured graphs
 static int set_comm_mode(dqnb_handle h, int mode) {
-  DQNB_CUDA(cudaStreamSynchronize(h->stream));
+  if (sync_all(h)) return -1;
   h->comm_mode = mode;
   if (mode != 2) for (int n = 0; n < 2; ++n) h->Gr[n] = h->G[n];
-  if (h->graph_sampled) { cudaGraphExecDestroy(h->graph_sampled); h->graph_sampled = nullptr; }
-  if (h->graph_injected) { cudaGraphExecDestroy(h->graph_injected); h->graph_injected = nullptr; }
+  for (int i = 0; i < 2; ++i) if (h->graph[i]) { cudaGraphExecDestroy(h->graph[i]); h->graph[i] = nullptr; }
   if (build_update_ops(h)) return -1;
   attach_trace(h);
   return 0;
@@ -1667,11 +1881,9 @@ int dqnb_comm_p2p_init(dqnb_handle h, const void *handles) {
 int dqnb_comm_status(dqnb_handle h) {
   if (!h) return -1;
   if (!h->p2p_err) return 0;
-  int e = 0;
   cudaSetDevice(h->cfg.device);
   cudaStreamSynchronize(h->stream);
-  if (cudaMemcpy(&e, h->p2p_err, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
-  return e;
+  return h->h_p2p_err ? *h->h_p2p_err : 0;
 }
 
 int dqnb_sync(dqnb_handle h) {

@@ -57,43 +57,13 @@ struct HyperParams {
   float inv_batch_global;           // 1 / (batch * world_size): EuclideanLoss 1/N
 };
 
-// -------------------------------------------------------------------------------------------
-__global__ void prep_kernel(StepState *st, HyperParams hp) {
-  DQNB_PDL_PROLOGUE();
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  // AdamSolver::ComputeUpdateValue: t = iter + 1; correction evaluated in double (std::pow(float,int))
-  const int tc = st->critic_iter + 1, ta = st->actor_iter + 1;
-  const double b1 = (double)hp.beta1, b2 = (double)hp.beta2;
-  const float cc = (float)(sqrt(1.0 - pow(b2, (double)tc)) / (1.0 - pow(b1, (double)tc)));
-  const float ca = (float)(sqrt(1.0 - pow(b2, (double)ta)) / (1.0 - pow(b1, (double)ta)));
-  st->step_critic = __fmul_rn(hp.critic_lr, cc);
-  st->step_actor = __fmul_rn(hp.actor_lr, ca);
-  const int mx = max(ta, tc);       // max_iter() after both solvers stepped (dqn.cpp:967)
-  st->do_soft = (hp.soft_update_freq > 0 && mx % hp.soft_update_freq == 0) ? 1 : 0;
-}
-
-__global__ void finalize_kernel(StepState *st, const float *g_critic_tail, const float *g_actor_tail,
-                                float *results, int max_slots) {
-  DQNB_PDL_PROLOGUE();
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  const int slot = st->result_slot;
-  if (slot < max_slots) {
-    results[2 * slot + 0] = g_critic_tail[0];   // critic_loss (dqn.cpp:905)
-    results[2 * slot + 1] = g_actor_tail[0];    // avg_q       (dqn.cpp:915)
-  }
-  st->result_slot = slot + 1;
-  st->critic_iter += 1;                         // Solver::Step ++iter_ (dqn.cpp:904)
-  st->actor_iter += 1;                          // set_iter(iter+1)     (dqn.cpp:965)
-  st->step += 1;
-}
-
 // SampleTransitionsFromMemory (dqn.cpp:501-509): B uniform draws with replacement in [0,size)
-__global__ void sample_kernel(const StepState *st, unsigned long long seed, int B, int32_t *idx) {
+__global__ void sample_kernel(const StepState *st, unsigned long long seed, unsigned long long step, int B, int32_t *idx) {
   DQNB_PDL_PROLOGUE();
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= B) return;
   const int size = st->ring_size;
-  idx[n] = size > 0 ? sample_index(seed, st->step, (uint32_t)n, (uint32_t)size) : 0;
+  idx[n] = size > 0 ? sample_index(seed, step, (uint32_t)n, (uint32_t)size) : 0;
 }
 
 // -------------------------------------------------------------------------------------------
@@ -104,6 +74,8 @@ struct GatherArgs {
   int32_t *idx;                // deque indices of the minibatch rows
   int sample;                  // 1: draw idx on the device (SampleTransitionsFromMemory, dqn.cpp:501-509)
   unsigned long long seed;
+  unsigned long long step;     // update counter keying the sampler (host mirror of StepState::step: the gather of update
+                               // t may run beside update t-1, whose last kernel advances the device counter)
   HyperParams hp;
   const float *ring_s, *ring_sn, *ring_misc;   // one row-interleaved ring: [state Sp | next Sp | misc 16]
   int rw;                      // floats per ring row
@@ -118,26 +90,13 @@ __global__ void __launch_bounds__(128) gather_kernel(const GatherArgs a) {
   trace_begin(a.trace);
   const int n = blockIdx.x;
   const bool valid = n < a.B;
-  if (n == 0 && threadIdx.x == 32) {
-    // per-update scalars (formerly a kernel of their own).  AdamSolver::ComputeUpdateValue: t = iter+1,
-    // correction evaluated in double (std::pow(float,int) promotes); consumed much later by adam_kernel.
-    StepState *st = a.st;
-    const int tc = st->critic_iter + 1, ta = st->actor_iter + 1;
-    const double b1 = (double)a.hp.beta1, b2 = (double)a.hp.beta2;
-    const float cc = (float)(sqrt(1.0 - pow(b2, (double)tc)) / (1.0 - pow(b1, (double)tc)));
-    const float ca = (float)(sqrt(1.0 - pow(b2, (double)ta)) / (1.0 - pow(b1, (double)ta)));
-    st->step_critic = __fmul_rn(a.hp.critic_lr, cc);
-    st->step_actor = __fmul_rn(a.hp.actor_lr, ca);
-    const int mx = max(ta, tc);       // max_iter() after both solvers stepped (dqn.cpp:967)
-    st->do_soft = (a.hp.soft_update_freq > 0 && mx % a.hp.soft_update_freq == 0) ? 1 : 0;
-  }
   long long phys = 0;
   float misc_term = 1.f;
   if (valid) {
     int id;
     if (a.sample) {
       const int size = a.st->ring_size;
-      id = size > 0 ? sample_index(a.seed, a.st->step, (uint32_t)n, (uint32_t)size) : 0;
+      id = size > 0 ? sample_index(a.seed, a.step, (uint32_t)n, (uint32_t)size) : 0;
       if (threadIdx.x == 0) a.idx[n] = id;
     } else {
       id = a.idx[n];
@@ -537,6 +496,8 @@ struct ReduceArgs {
   float *norm_part;            // per-block sum of squares
   const double *scal_part; int n_scal; float scal_scale;   // tail[0] = scale * sum(scal_part)
   int do_reduce, do_sumsq;
+  // the critic's reduction (first optimiser kernel of an update) also refreshes the per-update Adam scalars
+  int do_prep; StepState *st; HyperParams hp;
 };
 __global__ void __launch_bounds__(256) reduce_kernel(const ReduceArgs a) {
   DQNB_PDL_PROLOGUE();
@@ -585,6 +546,19 @@ __global__ void __launch_bounds__(256) reduce_kernel(const ReduceArgs a) {
     for (int j = 0; j < a.n_scal; ++j) s += a.scal_part[j];
     a.G[a.flat] = (float)(s * (double)a.scal_scale);
   }
+  if (a.do_prep && blockIdx.x == 0 && threadIdx.x == 32) {
+    // AdamSolver::ComputeUpdateValue: t = iter+1, correction evaluated in double (std::pow(float,int) promotes);
+    // consumed by both adam_kernel launches of this update
+    StepState *st = a.st;
+    const int tc = st->critic_iter + 1, ta = st->actor_iter + 1;
+    const double b1 = (double)a.hp.beta1, b2 = (double)a.hp.beta2;
+    const float cc = (float)(sqrt(1.0 - pow(b2, (double)tc)) / (1.0 - pow(b1, (double)tc)));
+    const float ca = (float)(sqrt(1.0 - pow(b2, (double)ta)) / (1.0 - pow(b1, (double)ta)));
+    st->step_critic = __fmul_rn(a.hp.critic_lr, cc);
+    st->step_actor = __fmul_rn(a.hp.actor_lr, ca);
+    const int mx = max(ta, tc);       // max_iter() after both solvers stepped (dqn.cpp:967)
+    st->do_soft = (a.hp.soft_update_freq > 0 && mx % a.hp.soft_update_freq == 0) ? 1 : 0;
+  }
   trace_end(a.trace);
 }
 
@@ -604,8 +578,15 @@ struct AdamArgs {
   // (critic_loss, avg_q) and advances the iteration / sampler counters (formerly finalize_kernel)
   int finalize; unsigned int *ticket; const float *g_critic_tail, *g_actor_tail; float *results; int max_slots;
   unsigned long long *done;         // mapped pinned word: number of finished updates (dqnb_results polls it)
+  // actor only: fp32 snapshot of the updated weights for the act path, written into buffer 1 - *act_cur;
+  // the finalize step flips *act_cur once every block of the update has retired
+  float *snap; long long snap_stride; unsigned int *act_cur;
+  // data-parallel runs: sticky flag of the gradient exchange (a peer missed its timeout).  Once set the reduced
+  // gradient is not trustworthy: no parameter, moment or iteration counter moves any more, the update only reports
+  // NaN results and advances the sequence number the host waits on.
+  const int *comm_err;
 };
-__device__ __forceinline__ void adam_finalize(const AdamArgs &a) {
+__device__ __forceinline__ void adam_finalize(const AdamArgs &a, bool failed) {
   __threadfence();
   __syncthreads();
   if (threadIdx.x != 0) return;
@@ -614,11 +595,14 @@ __device__ __forceinline__ void adam_finalize(const AdamArgs &a) {
   *a.ticket = 0;
   StepState *st = a.st_out;
   const int slot = (int)(st->step % (unsigned long long)a.max_slots);   // host-visible ring (mapped pinned memory)
-  a.results[2 * slot + 0] = a.g_critic_tail[0];     // critic_loss (dqn.cpp:905)
-  a.results[2 * slot + 1] = a.g_actor_tail[0];      // avg_q       (dqn.cpp:915)
-  st->critic_iter += 1;                             // Solver::Step ++iter_ (dqn.cpp:904)
-  st->actor_iter += 1;                              // set_iter(iter+1)     (dqn.cpp:965)
+  a.results[2 * slot + 0] = failed ? __int_as_float(0x7fc00000) : a.g_critic_tail[0];     // critic_loss (dqn.cpp:905)
+  a.results[2 * slot + 1] = failed ? __int_as_float(0x7fc00000) : a.g_actor_tail[0];      // avg_q       (dqn.cpp:915)
+  if (!failed) {
+    st->critic_iter += 1;                           // Solver::Step ++iter_ (dqn.cpp:904)
+    st->actor_iter += 1;                            // set_iter(iter+1)     (dqn.cpp:965)
+  }
   st->step += 1;
+  if (a.act_cur && !failed) { *a.act_cur ^= 1u; __threadfence(); }   // the snapshot the actor's blocks just wrote becomes current
   if (a.done) {
     __threadfence_system();                         // results first, then the counter the host spins on
     *reinterpret_cast<volatile unsigned long long *>(a.done) = st->step;
@@ -629,6 +613,11 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamArgs a) {
   trace_begin(a.trace);
   __shared__ float s_scale;
   __shared__ double red[8];
+  if (a.comm_err && *reinterpret_cast<const volatile int *>(a.comm_err) != 0) {   // uniform over the grid: set before this launch
+    if (a.finalize) adam_finalize(a, true);
+    trace_end(a.trace);
+    return;
+  }
   {
     double s = 0.0;
     for (int j = threadIdx.x; j < a.n_norm; j += blockDim.x) s += (double)a.norm_part[j];
@@ -649,7 +638,7 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamArgs a) {
   // from HBM: it is bandwidth-bound as it stands.)
   const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i >= a.flat) {
-    if (a.finalize) adam_finalize(a);
+    if (a.finalize) adam_finalize(a, false);
     trace_end(a.trace);
     return;
   }
@@ -681,6 +670,8 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamArgs a) {
   *reinterpret_cast<float4 *>(a.V + i) = make_float4(v[0], v[1], v[2], v[3]);
   *reinterpret_cast<float4 *>(a.P + i) = make_float4(wh[0], wh[1], wh[2], wh[3]);
   *reinterpret_cast<float4 *>(a.P + a.p_plane + i) = make_float4(wl[0], wl[1], wl[2], wl[3]);
+  if (a.snap)
+    *reinterpret_cast<float4 *>(a.snap + (long long)((*a.act_cur & 1u) ^ 1u) * a.snap_stride + i) = make_float4(w[0], w[1], w[2], w[3]);
   if (do_soft) {
     const float4 th = *reinterpret_cast<const float4 *>(a.T + i);
     const float4 tl = *reinterpret_cast<const float4 *>(a.T + a.t_plane + i);
@@ -696,7 +687,7 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamArgs a) {
     *reinterpret_cast<float4 *>(a.T + i) = make_float4(oh[0], oh[1], oh[2], oh[3]);
     *reinterpret_cast<float4 *>(a.T + a.t_plane + i) = make_float4(ol[0], ol[1], ol[2], ol[3]);
   }
-  if (a.finalize) adam_finalize(a);
+  if (a.finalize) adam_finalize(a, false);
   trace_end(a.trace);
 }
 
@@ -725,7 +716,8 @@ struct P2PArgs {
   long long count;                // floats to reduce (multiple of 4)
   unsigned int *epoch;            // [2] per net, local memory
   unsigned int *ticket;           // [2] per net, local memory
-  int *err;
+  int *err;                       // host-mapped, sticky
+  unsigned long long timeout_ns;
 };
 __device__ __forceinline__ unsigned int ld_acquire_sys_u32(const unsigned int *p) {
   unsigned int v;
@@ -740,13 +732,15 @@ __device__ __forceinline__ float4 ld_volatile_f4(const float *p) {
   asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ bool spin_until_ge(const unsigned int *flag, unsigned int target, int *err) {
+__device__ __forceinline__ bool spin_until_ge(const unsigned int *flag, unsigned int target, int *err, unsigned long long timeout_ns) {
   unsigned long long t0;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
   while (ld_acquire_sys_u32(flag) < target) {
     unsigned long long t1;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
-    if (t1 - t0 > 2000000000ull) { *err = 1; return false; }   // 2 s: a peer is gone; give up instead of hanging
+    // a peer is gone (or later than DQNB_P2P_TIMEOUT_MS): give up instead of hanging the GPU.  The flag is sticky and
+    // host-visible: the optimiser kernels skip their update once it is set and dqnb_update / dqnb_results fail.
+    if (t1 - t0 > timeout_ns) { *reinterpret_cast<volatile int *>(err) = 1; __threadfence_system(); return false; }
     __nanosleep(64);
   }
   return true;
@@ -766,7 +760,7 @@ __global__ void __launch_bounds__(512) p2p_allreduce_kernel(const P2PArgs a) {
     unsigned int *pf = reinterpret_cast<unsigned int *>(a.tab->base[threadIdx.x] + a.flag_off) + a.net * kMaxPeers;
     st_release_sys_u32(pf + a.rank, e);
   }
-  if (threadIdx.x < W) spin_until_ge(my_flagA + threadIdx.x, e, a.err);
+  if (threadIdx.x < W) spin_until_ge(my_flagA + threadIdx.x, e, a.err, a.timeout_ns);
   __syncthreads();
   // B
   const long long n4 = a.count / 4, per = (n4 + W - 1) / W;
@@ -830,10 +824,88 @@ __global__ void __launch_bounds__(512) p2p_allreduce_kernel(const P2PArgs a) {
     __threadfence_system();
     unsigned int *pf = reinterpret_cast<unsigned int *>(a.tab->base[threadIdx.x] + a.flag_off) + 2 * kMaxPeers + a.net * kMaxPeers;
     st_release_sys_u32(pf + a.rank, e);
-    spin_until_ge(my_flagB + threadIdx.x, e, a.err);
+    spin_until_ge(my_flagB + threadIdx.x, e, a.err, a.timeout_ns);
   }
   __syncthreads();
   if (threadIdx.x == 0) { a.ticket[a.net] = 0; a.epoch[a.net] = e; __threadfence(); }
+}
+
+// -------------------------------------------------------------------------------------------
+// Act path: SelectActionGreedily on a handful of states (dqn.cpp:734-766; one call per environment step per agent,
+// dqn_main.cpp:123).  Latency-bound, so it never touches the learner's stream: it runs as its own captured graph on a
+// high-priority stream and reads a SNAPSHOT of the actor (plain fp32, internal padded layout) that the actor's
+// adam_kernel writes beside the learner's split planes - into the buffer the act path is not reading - and publishes
+// by flipping *cur when the update is complete.  Rows travel through host-mapped pinned memory in both directions and
+// completion is a sequence number the host spins on: no stream synchronisation, no cudaMemcpy.
+// Skinny M (1..kActMaxRows rows): one warp per output feature, lanes along K, 8 rows of accumulators per pass, the
+// weights (3 MB, L2-resident) are read once per 8 rows.  FP32 FFMA: 0.75 MFLOP per row is far below any roofline.
+constexpr int kActMaxRows = 64;
+constexpr int kActRowGroup = 8;
+constexpr int kActHdr = 4;         // floats of header in front of the staged rows: {n, seq, -, -} as 32-bit integers
+struct ActCtl {                    // host-mapped pinned completion block (written by the device with posted PCIe writes)
+  volatile unsigned int done;      // seq of the last finished call
+  unsigned int cur_used;           // snapshot buffer that call read (diagnostics)
+};
+// The call's header and rows arrive in device memory by one DMA (a memcpy node at the head of the act graph): kernels
+// never READ host memory - a sysmem read costs ~1 us and they serialise (measured: 128 blocks polling a mapped word
+// made the first layer 0.9 ms long).
+struct ActStageArgs {
+  const unsigned int *cur; unsigned int *sel;   // latches the snapshot choice of this call for all its layers
+};
+__global__ void act_stage_kernel(const ActStageArgs a) {
+  DQNB_PDL_PROLOGUE();
+  if (threadIdx.x == 0) *a.sel = *reinterpret_cast<const volatile unsigned int *>(a.cur) & 1u;
+}
+struct ActLayerArgs {
+  ActCtl *ctl; const int *hdr;             // hdr: device copy of {n, seq}
+  const float *snap; long long snap_stride; const unsigned int *sel;   // weights: snap + sel * stride
+  long long w_off, b_off; int Kp, N;       // W [N x Kp] row-major, b [N]
+  const float *X; int ldx; float *Y; int ldy;
+  int lrelu;
+  int last; float *h_out;                  // last layer: rows go to mapped host memory [n][16], then ctl->done = seq
+};
+__global__ void __launch_bounds__(512) act_layer_kernel(const ActLayerArgs a) {
+  DQNB_PDL_PROLOGUE();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j = blockIdx.x * (int)(blockDim.x >> 5) + warp;
+  const int n = min(max(a.hdr[0], 0), kActMaxRows);
+  const float *P = a.snap + (long long)(*a.sel) * a.snap_stride;
+  if (j < a.N) {
+    const float *w = P + a.w_off + (long long)j * a.Kp;
+    const float bias = P[a.b_off + j];
+    for (int r0 = 0; r0 < n; r0 += kActRowGroup) {
+      float acc[kActRowGroup];
+#pragma unroll
+      for (int r = 0; r < kActRowGroup; ++r) acc[r] = 0.f;
+      for (int k = lane * 4; k < a.Kp; k += 128) {
+        const float4 w4 = ld4(w + k);
+#pragma unroll
+        for (int r = 0; r < kActRowGroup; ++r)
+          if (r0 + r < n) acc[r] = dot4(*reinterpret_cast<const float4 *>(a.X + (long long)(r0 + r) * a.ldx + k), w4, acc[r]);
+      }
+#pragma unroll
+      for (int r = 0; r < kActRowGroup; ++r) acc[r] = warp_sum(acc[r]);
+      if (lane < kActRowGroup && r0 + lane < n) {
+        float v = 0.f;
+#pragma unroll
+        for (int r = 0; r < kActRowGroup; ++r)
+          if (r == lane) v = acc[r];
+        v += bias;
+        if (a.lrelu) v = fmaxf(v, 0.f) + kNegSlope * fminf(v, 0.f);
+        if (a.last) a.h_out[(long long)(r0 + lane) * 16 + j] = v;
+        else a.Y[(long long)(r0 + lane) * a.ldy + j] = v;
+      }
+    }
+  }
+  if (a.last) {          // launched as ONE block of 512 threads (N <= 16, checked by the host): publish completion
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      a.ctl->cur_used = *a.sel;
+      __threadfence_system();
+      a.ctl->done = (unsigned int)a.hdr[1];
+    }
+  }
 }
 
 // split an fp32 array into (hi, lo) planes / join it back (parameter import / export)
