@@ -389,9 +389,15 @@ struct Tuning {
                     //    pass instead of beside the target critic, which then runs alone with cluster split-K
   int cluster_b;    // 1: cluster split-K also for the target chains, which share the machine with the side chains
   int pdl_early;    // GEMM kernels: 1 = launch_dependents right after the wait, 0 = after the last MMA issue
+  int store_wait_full;   // GEMM epilogue: 1 = cp.async.bulk.wait_group (stores written), 0 = .read (staging released)
+  int side_delay;   // 1: a side chain of the forward phase starts when the critical chain's first (machine-filling) layer
+                    //    of the same pair has finished, and the actor's chain joins only before its consumer
   int bn_big;       // 128: dX / dW GEMMs that fill the machine with 128x64 tiles anyway use 128x128 tiles (half the CTAs,
                     //      1.6x the tensor rate per CTA), so the two big GEMMs of a backward pass run side by side
   int bn_fwd, bn_fwd_side, bn_dx, bn_dw;   // N tile (64 / 128) per GEMM class
+  int dw_after_dx;  // bit l: the weight-gradient GEMM of tower layer l waits for the end of the dX chain (dZ[0])
+  int bn_side_l1;   // N tile of a side chain's first layer: 128 halves its CTA count (128 -> 64), so that it fits beside
+                    // the critical chain's second layer (64 CTAs) instead of queueing in front of it
   int st_fwd, st_fwd_side, st_dx, st_dw;   // smem ring depth per GEMM class (0 = deepest that fits)
   Tuning() {
     sched = env_int("DQNB_SCHED", 1);
@@ -401,9 +407,13 @@ struct Tuning {
     actor_late = env_int("DQNB_ACTOR_LATE", 0);
     cluster_b = env_int("DQNB_CLUSTER_B", 0);
     pdl_early = env_int("DQNB_PDL_EARLY", 0);
+    store_wait_full = env_int("DQNB_STORE_WAIT_FULL", 0);
+    side_delay = env_int("DQNB_SIDE_DELAY", 1);
     bn_big = env_int("DQNB_BN_BIG", 64);
     bn_fwd = env_int("DQNB_BN_FWD", 64);
     bn_fwd_side = env_int("DQNB_BN_FWD_SIDE", 64);
+    dw_after_dx = env_int("DQNB_DW_AFTER_DX", 0);
+    bn_side_l1 = env_int("DQNB_BN_SIDE_L1", 128);
     bn_dx = env_int("DQNB_BN_DX", 64);
     bn_dw = env_int("DQNB_BN_DW", 128);   // 128-wide tiles, twice the splits: half the mainloop per CTA in the tail of a pass
     st_fwd = env_int("DQNB_ST_FWD", 0);
@@ -436,6 +446,7 @@ static int finish_gemm(const dqnb_config &cfg, Op *op) {
     if (p.bn != 64 && p.bn != 128) p.bn = 64;
     if (p.stages < 2 || p.stages > tc_max_stages(p.bn)) p.stages = tc_max_stages(p.bn);
     p.pdl_early = tuning().pdl_early;
+    p.store_wait_full = tuning().store_wait_full;
     if (p.epi == EPI_DX && !p.relu_bits_in) DQNB_FAIL("EPI_DX needs the sign bits of the saved activation");
     // Forward / dX GEMMs with a long contraction but few output tiles: split K over a 2-CTA cluster
     // (DSMEM reduction in the epilogue) so that the dependent chain sees half the mainloop latency.
@@ -571,7 +582,9 @@ static int launch_op(dqnb_handle_s *h, const Op &op, cudaStream_t s) {
     case Op::GEMM:
       if (h->cfg.gemm_mode == DQNB_GEMM_TCGEN05_3XTF32) {
         g_cluster_z = op.gemm.p.cluster_k ? 2 : 1;
-        e = launch_k(tc_kernel_for(op.gemm.p.a_mn, op.gemm.p.b_mn, op.gemm.p.bn), op.grid, dim3(TC_THREADS),
+        TcKernel k = tc_kernel_for(op.gemm.p.a_mn, op.gemm.p.b_mn, op.gemm.p.bn, op.gemm.p.epi);
+        if (!k) DQNB_FAIL("no tcgen05 kernel instance for operand layout (%d,%d) with epilogue %d", op.gemm.p.a_mn, op.gemm.p.b_mn, op.gemm.p.epi);
+        e = launch_k(k, op.grid, dim3(TC_THREADS),
                      (size_t)tc_smem_for(op.gemm.p.bn, op.gemm.p.stages), s, op.gemm);
         g_cluster_z = 1;
       }
@@ -644,7 +657,7 @@ static int build_forward(dqnb_handle_s *h, const NetGeom &g, const float *P, con
   const SplitMat *in = &X;
   for (int l = 0; l < g.n_hidden; ++l) {
     Op op;
-    if (op_fwd(h->cfg, g, l, P, *in, acts[l], &op, critical_chain ? tuning().bn_fwd : tuning().bn_fwd_side,
+    if (op_fwd(h->cfg, g, l, P, *in, acts[l], &op, critical_chain ? tuning().bn_fwd : (l == 0 ? tuning().bn_side_l1 : tuning().bn_fwd_side),
                critical_chain ? tuning().st_fwd : tuning().st_fwd_side)) return -1;
     if ((!critical_chain || !allow_cluster) && op.gemm.p.cluster_k) {
       // side-branch passes run beside the critical chain: they should not grab twice the SMs for a
@@ -695,6 +708,7 @@ static int build_backward(dqnb_handle_s *h, const NetGeom &g, const float *P, co
     Op f; f.kind = Op::FORK; f.mask = fork_mask; ops.push_back(f);
     if (head_bwd_w) { Op w = *head_bwd_w; w.branch = 2; ops.push_back(w); }
   }
+  std::vector<Op> deferred;
   for (int l = top; l >= 0; --l) {
     if (want_dw) {
       Op op;
@@ -702,14 +716,18 @@ static int build_backward(dqnb_handle_s *h, const NetGeom &g, const float *P, co
       if (op_dw(h->cfg, g, l, h->dZ[l], l > 0 ? acts[l - 1] : X, h->Gpart[g.critic], h->gpart_stride[g.critic], &splits, &op)) return -1;
       op.branch = 3 + l;
       if (l < top) op.wait_ev = l;                              // dZ[l] is produced by the dX op below
-      ops.push_back(op);
+      // the big weight-gradient GEMMs of the middle layers become ready while the dX chain (critical path) still
+      // needs the whole machine for its widest layers; a CTA that is resident is never preempted, so they are held
+      // back until dZ[0] exists and then run beside the first layer's weight gradient (two CTAs per SM)
+      const bool held = l >= 1 && l < top && (tuning().dw_after_dx >> l & 1);
+      if (held) { op.wait_ev = 0; deferred.push_back(op); } else ops.push_back(op);
       const bool fused_here = fuse_cs && l < top;
       if (!fused_here) {
         // bias column sums of dZ[l] by a launch of their own: behind the weight gradient that waits for the same dZ;
         // the last two (whose GEMMs form the tail of the pass) beside their GEMMs on branch 2, after the head gradient
         Op c = make_colsum(h, g, l, l + 1);
         if (l > 1 || l == top) c.branch = 3 + l; else { c.branch = 2; c.wait_ev = l; }
-        ops.push_back(c);
+        if (held && c.branch == 3 + l) deferred.push_back(c); else ops.push_back(c);   // stays behind its weight gradient
       }
       // segment table entries (internal flat order: W_l then b_l)
       SegTable &T = *segs;
@@ -725,6 +743,7 @@ static int build_backward(dqnb_handle_s *h, const NetGeom &g, const float *P, co
       if (want_dw) op.rec_ev = l - 1;                           // dZ[l-1] ready
       if (fuse_cs) { op.gemm.p.colsum_out = h->Bpart[g.critic] + h->boff[l - 1]; op.gemm.p.colsum_stride = h->bflat; }
       ops.push_back(op);
+      if (l == 1) { ops.insert(ops.end(), deferred.begin(), deferred.end()); deferred.clear(); }   // event 0 now exists
     }
   }
   if (want_dw) {
@@ -858,11 +877,24 @@ static int build_update_ops_for(dqnb_handle_s *h, int set) {
   const int side2 = getenv("DQNB_SIDE_SERIAL") ? 1 : 2;
   const int fork_mask = sched == 1 ? 1 : (side2 == 2 ? 3 : 1);
   constexpr int kEvActorStart = 7;
+  const bool side_delay = sched == 1 && tuning().side_delay != 0 && !tuning().actor_late;
+  constexpr int kEvCriticStart = 6;
   op.kind = Op::FORK; op.mask = fork_mask; ops.push_back(op);
+  std::vector<Op> ta_ops;                           // target actor tower (main stream)
+  if (build_forward(h, gA, PAT, h->Xsn, h->actAT, ta_ops, true, tuning().cluster_b != 0)) return -1;
+  if (side_delay) {
+    // The first layer of a tower fills the machine (128 CTAs) for a few microseconds.  Launched together, the side
+    // chain's first layer takes the SMs the critical chain's next layer needs (measured: +5 us on each pair), so the
+    // side chain starts when the critical chain's first layer is done.
+    ta_ops[0].rec_ev = kEvCriticStart;
+    ops.push_back(ta_ops[0]);
+    ta_ops.erase(ta_ops.begin());
+  }
   {
     const size_t mark = ops.size();
     if (build_forward(h, gC, PC, h->Xc, h->actC, ops, false)) return -1;
     for (size_t i = mark; i < ops.size(); ++i) ops[i].branch = 1;
+    if (side_delay) ops[mark].wait_ev = kEvCriticStart;
   }
   auto push_actor_chain = [&](int branch, int wait_ev) -> int {
     const size_t mark = ops.size();
@@ -875,14 +907,24 @@ static int build_update_ops_for(dqnb_handle_s *h, int set) {
   };
   if (sched != 1 && push_actor_chain(side2, -1)) return -1;   // same side stream: at most two chains compete
   op.branch = 0;
-  if (build_forward(h, gA, PAT, h->Xsn, h->actAT, ops, true, tuning().cluster_b != 0)) return -1;
+  ops.insert(ops.end(), ta_ops.begin(), ta_ops.end());
   op_head_fwd(gA, PAT, h->actAT[topA], h->B, h->a16_t, &h->Xct, h->S, &op);
   const bool actor_late = sched == 1 && tuning().actor_late;
   constexpr int kLateBranch = 8;                  // a side stream nothing else uses
-  if (sched == 1 && !actor_late) op.rec_ev = kEvActorStart;
+  if (sched == 1 && !actor_late && !side_delay) op.rec_ev = kEvActorStart;
   ops.push_back(op);
   op.rec_ev = -1;
-  if (sched == 1 && !actor_late && push_actor_chain(2, kEvActorStart)) return -1;
+  if (sched == 1 && !actor_late && !side_delay && push_actor_chain(2, kEvActorStart)) return -1;
+  if (side_delay) {
+    // target critic: first layer, then the actor's chain starts on a stream of its own; it is joined with the critic's
+    // gradient branches (its consumer is the critic forward on (s, a_pi), after the critic's optimiser step)
+    std::vector<Op> tc_ops;
+    if (build_forward(h, gC, PCT, h->Xct, h->actCT, tc_ops, true, tuning().cluster_b != 0)) return -1;
+    tc_ops[0].rec_ev = kEvActorStart;
+    ops.push_back(tc_ops[0]);
+    if (push_actor_chain(kLateBranch, kEvActorStart)) return -1;
+    ops.insert(ops.end(), tc_ops.begin() + 1, tc_ops.end());
+  } else
   if (build_forward(h, gC, PCT, h->Xct, h->actCT, ops, true, tuning().cluster_b != 0 || actor_late)) return -1;
   if (tuning().fuse_tl) {
     // dqn.cpp:892-900 TD target and the head of critic_solver_->Step(1) (loss + head backward) in one launch
@@ -902,7 +944,7 @@ static int build_update_ops_for(dqnb_handle_s *h, int set) {
     if (push_actor_chain(kLateBranch, kEvActorStart)) return -1;
   }
   Op hbw = make_head_bwd_w(h, gC, h->d16c, h->actC[topC]);
-  if (build_backward(h, gC, PC, h->Xc, h->actC, true, &h->segs[1], &hbw, ops, actor_late ? 1 << (kLateBranch - 1) : 0)) return -1;
+  if (build_backward(h, gC, PC, h->Xc, h->actC, true, &h->segs[1], &hbw, ops, (actor_late || side_delay) ? 1 << (kLateBranch - 1) : 0)) return -1;
   build_solver(h, 1, h->segs[1], 0.5f * h->hp.inv_batch_global, ops);
   // dqn.cpp:913-916 critic forward on (s, a_pi) with the updated critic
   if (build_forward(h, gC, PC, h->Xcp, h->actC, ops)) return -1;
@@ -1661,16 +1703,29 @@ int dqnb_benchmark_gemms(dqnb_handle h, int32_t reps, float *ms_per_update, int3
   DQNB_CUDA(cudaSetDevice(h->cfg.device));
   int n = 0;
   for (const Op &op : h->update_ops) if (op.kind == Op::GEMM) ++n;
-  DQNB_CUDA(cudaStreamSynchronize(h->stream));
+  if (sync_all(h)) return -1;
+  // one update's GEMM launches captured as a graph (eager launches of 38 kernels with 400-byte argument blocks are
+  // bound by the host, not by the device: 10-15 us per launch measured), replayed reps times between two events
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  DQNB_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+  int rc = 0;
+  for (const Op &op : h->update_ops)
+    if (op.kind == Op::GEMM && launch_op(h, op, h->stream)) { rc = -1; break; }
+  cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
+  if (rc) { if (graph) cudaGraphDestroy(graph); return -1; }
+  DQNB_CUDA(e);
+  DQNB_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+  DQNB_CUDA(cudaGraphDestroy(graph));
   for (int r = 0; r < reps + 2; ++r) {
     if (r == 2) DQNB_CUDA(cudaEventRecord(h->ev0, h->stream));
-    for (const Op &op : h->update_ops)
-      if (op.kind == Op::GEMM && launch_op(h, op, h->stream)) return -1;
+    DQNB_CUDA(cudaGraphLaunch(exec, h->stream));
   }
   DQNB_CUDA(cudaEventRecord(h->ev1, h->stream));
   DQNB_CUDA(cudaEventSynchronize(h->ev1));
   float ms = 0.f;
   DQNB_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  DQNB_CUDA(cudaGraphExecDestroy(exec));
   *ms_per_update = ms / reps;
   if (gemm_launches) *gemm_launches = n;
   h->launches += (int64_t)n * (reps + 2);
@@ -2000,7 +2055,7 @@ int dqnb_gemm_test(int device, int gemm_mode, int a_mn, int b_mn, int M, int N, 
     if (r == 1) DQNB_CUDA(cudaEventRecord(e0, 0));
     p.dbg_clk = dclk + kTraceSlots * r;            // per-launch timeline slot
     if (gemm_mode == DQNB_GEMM_TCGEN05_3XTF32)
-      DQNB_CUDA(launch_k(tc_kernel_for(a_mn, b_mn, p.bn), op.grid, dim3(TC_THREADS), (size_t)tc_smem_for(p.bn, p.stages), (cudaStream_t)0, op.gemm));
+      DQNB_CUDA(launch_k(tc_kernel_for(a_mn, b_mn, p.bn, EPI_PLAIN), op.grid, dim3(TC_THREADS), (size_t)tc_smem_for(p.bn, p.stages), (cudaStream_t)0, op.gemm));
     else gemm_simt_kernel<<<op.grid, 256>>>(op.gemm.p);
   }
   DQNB_CUDA(cudaEventRecord(e1, 0));

@@ -54,6 +54,7 @@ struct GemmParams {
                                               //    then sit on SMs - 197 KB of smem each - for this kernel's whole
                                               //    duration); 0: when the last MMA has been issued, so they only overlap
                                               //    the accumulator drain + epilogue (measured: profiles/r01c_*)
+  int store_wait_full;                        // 1: the epilogue waits for its TMA stores to be written, not just read (A/B knob)
   int dbg;                                    // perf experiments (gemm_test only): bit0 skip MMA, bit1 skip TMA
   long long *dbg_clk;                         // optional: MMA-thread clock64 stamps {start, issued, complete}
 };
@@ -241,6 +242,9 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap *tm, uint32_t src
                : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// .read: wait until the staged boxes have been READ out of shared memory (it may then be released); the writes
+// themselves complete before the grid does, which is what griddepcontrol.wait / stream order of the consumer wait for
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void st_smem_f4(uint32_t addr, float a, float b, float c, float d) {
@@ -328,7 +332,7 @@ __device__ __forceinline__ float4 ld_dsmem_f4(uint32_t local_saddr, uint32_t ran
 // warp-uniform (uniform registers, no per-thread descriptor arithmetic), and one elected lane
 // issues.  A single divergent thread doing that arithmetic costs ~300 cycles per k-step, 3x the
 // tensor time of the three MMAs it feeds (measured: profiles/r01_gemm_issue_loop.md).
-template <int A_MN, int B_MN, int BN_>
+template <int A_MN, int B_MN, int BN_, int EPI_>
 __device__ __forceinline__ void gemm_tc_body(const GemmArgs &args, const int n_tile, const int m_tile, const int split) {
   using Cfg = TcCfg<BN_>;
   extern __shared__ uint8_t smem_raw[];
@@ -474,7 +478,7 @@ __device__ __forceinline__ void gemm_tc_body(const GemmArgs &args, const int n_t
     float *st_hi = reinterpret_cast<float *>(base_ptr) + (q * 32) * LDS;
     const int n_base = n_tile * BN_;
     const bool peer = clus && crank == 1;
-    if (warp >= 2 && !peer && p.epi == EPI_FWD) {    // stage the tile's bias once (overlaps the mainloop)
+    if (warp >= 2 && !peer && EPI_ == EPI_FWD) {    // stage the tile's bias once (overlaps the mainloop)
       for (int t = threadIdx.x - 64; t < BN_; t += TC_THREADS - 64) {
         const int n = n_base + t;
         s_bias[t] = (p.bias_hi && n < p.N) ? p.bias_hi[n] + p.bias_lo[n] : 0.f;
@@ -488,7 +492,7 @@ __device__ __forceinline__ void gemm_tc_body(const GemmArgs &args, const int n_t
     for (int i = 0; i < MYCH; ++i) {
       const int c0 = (half + 2 * i) * 32;
       rbits[i] = 0u;
-      if (!peer && p.epi == EPI_DX && m_row < p.M && n_base + c0 < p.N)
+      if (!peer && EPI_ == EPI_DX && m_row < p.M && n_base + c0 < p.N)
         rbits[i] = __ldg(p.relu_bits_in + (long long)m_row * p.ldbits + ((n_base + c0) >> 5));
     }
     asm volatile("bar.sync 1, %0;" ::"n"(TC_THREADS) : "memory");   // bias tile visible; warps 0/1 are done issuing
@@ -528,7 +532,7 @@ __device__ __forceinline__ void gemm_tc_body(const GemmArgs &args, const int n_t
       const float *peer_row = st_hi + lane * LDS;          // same offset inside the peer CTA's shared memory
       const uint32_t box0 = base + (uint32_t)(q * NCH) * 8192u;   // staging boxes: [quarter][chunk][plane][32 rows][128 B]
       const uint32_t row_off = (uint32_t)lane * 128u, sw = (uint32_t)(lane & 7);
-      const int planes_out = p.epi == EPI_PLAIN ? 1 : 2;
+      const int planes_out = EPI_ == EPI_PLAIN ? 1 : 2;
 #pragma unroll
       for (int i = 0; i < MYCH; ++i) {
         const int c0 = (half + 2 * i) * 32;
@@ -538,6 +542,7 @@ __device__ __forceinline__ void gemm_tc_body(const GemmArgs &args, const int n_t
         uint32_t bits_out = 0u;
         if (iters > 0) {
           tmem_wait_ld();
+          if (i == 0 && warp == 2 && lane == 0) DQNB_STAMP(11);       // first accumulator chunk in registers
           if (i + 1 < MYCH) {              // next chunk in flight while this one is processed
             tmem_ld32(taddr0 + (uint32_t)(c0 + 64), ra[cur ^ 1]);
             tmem_ld32(taddr0 + (uint32_t)(c0 + 64) + BN_, rb[cur ^ 1]);
@@ -557,7 +562,7 @@ __device__ __forceinline__ void gemm_tc_body(const GemmArgs &args, const int n_t
           }
         }
         const uint32_t box = box0 + (uint32_t)(c0 >> 5) * 8192u + row_off;
-        if (p.epi == EPI_PLAIN) {
+        if (EPI_ == EPI_PLAIN) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4)
             st_smem_f4(box + ((((uint32_t)j >> 2) ^ sw) << 4), v[j], v[j + 1], v[j + 2], v[j + 3]);
@@ -566,14 +571,14 @@ __device__ __forceinline__ void gemm_tc_body(const GemmArgs &args, const int n_t
           for (int j = 0; j < 32; j += 4) {
             float o[4], l[4];
             float4 aux = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p.epi == EPI_FWD) aux = *reinterpret_cast<const float4 *>(s_bias + c0 + j);
+            if (EPI_ == EPI_FWD) aux = *reinterpret_cast<const float4 *>(s_bias + c0 + j);
             const float ax[4] = {aux.x, aux.y, aux.z, aux.w};
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
               float x = v[j + t];
-              if (p.epi == EPI_FWD) {
+              if (EPI_ == EPI_FWD) {
                 x += ax[t];                                            // InnerProduct bias
-                if (p.apply_lrelu) x = fmaxf(x, 0.f) + kNegSlope * fminf(x, 0.f);
+                if (p.apply_lrelu) x = fmaxf(x, kNegSlope * x);        // == max(x,0) + slope * min(x,0) (Caffe ReLU), one op less
                 bits_out |= (x > 0.f ? 1u : 0u) << (j + t);            // sign of the in-place activation
               } else {
                 x *= ((bits_in >> (j + t)) & 1u) ? 1.f : kNegSlope;    // ReLU backward on the in-place activation
@@ -586,9 +591,9 @@ __device__ __forceinline__ void gemm_tc_body(const GemmArgs &args, const int n_t
             st_smem_f4(slot, o[0], o[1], o[2], o[3]);
             st_smem_f4(slot + 4096u, l[0], l[1], l[2], l[3]);
           }
-          if (p.epi == EPI_FWD && p.relu_bits_out && m_row < p.M && n_base + c0 < p.N)
+          if (EPI_ == EPI_FWD && p.relu_bits_out && m_row < p.M && n_base + c0 < p.N)
             p.relu_bits_out[(long long)m_row * p.ldbits + ((n_base + c0) >> 5)] = bits_out;
-          if (p.epi == EPI_DX && p.colsum_out) {
+          if (EPI_ == EPI_DX && p.colsum_out) {
             // column sums over this warp's 32 rows: halving butterfly, 31 shuffles; lane L ends up with column c0 + L
             // (bit b of the lane selects bit b of the column).  Fixed tree -> the same bits on every run.
             if (m_row >= p.M) {
@@ -611,19 +616,20 @@ __device__ __forceinline__ void gemm_tc_body(const GemmArgs &args, const int n_t
         // hand this chunk's box (both planes) to the TMA unit; the next chunk is staged meanwhile
         fence_proxy_async_smem();
         __syncwarp();
+        if (i == MYCH - 1 && warp == 2 && lane == 0) DQNB_STAMP(12);  // last box staged
         if (lane == 0 && n_base + c0 < p.N && m_tile * BM + q * 32 < p.M) {
           tma_store_3d(&args.tmD, box - row_off, n_base + c0, m_tile * BM + q * 32, planes_out == 1 ? split : 0);
           bulk_commit();
         }
       }
-      if (p.epi == EPI_DX && p.colsum_out) {
+      if (EPI_ == EPI_DX && p.colsum_out) {
         asm volatile("bar.sync 2, %0;" ::"n"(TC_THREADS) : "memory");   // every warp of this (non-peer) CTA is here
         if (threadIdx.x < BN_ && n_base + (int)threadIdx.x < p.N) {
           const float *c = s_colsum + threadIdx.x;
           p.colsum_out[(long long)m_tile * p.colsum_stride + n_base + threadIdx.x] = ((c[0] + c[BN_]) + c[2 * BN_]) + c[3 * BN_];
         }
       }
-      if (lane == 0) bulk_wait_all();          // the boxes have been read and written before shared memory goes away
+      if (lane == 0) { if (p.store_wait_full) bulk_wait_all(); else bulk_wait_read(); }   // the boxes have been read before shared memory goes away
       __syncwarp();
       if (warp == 2 && lane == 0) { DQNB_STAMP(5); DQNB_STAMP_MAX(10); }
     }
@@ -638,6 +644,7 @@ __device__ __forceinline__ void gemm_tc_body(const GemmArgs &args, const int n_t
   }
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) DQNB_STAMP(13);                                                  // CTA (0,0,0) past its last barrier
   if (p.dbg_clk && threadIdx.x == 0) atomicMax(p.dbg_clk + 6, (long long)gtime_ns());   // latest CTA exit of the grid
   if (warp == 1) {
     __syncwarp();
@@ -646,24 +653,28 @@ __device__ __forceinline__ void gemm_tc_body(const GemmArgs &args, const int n_t
   }
 }
 
-template <int A_MN, int B_MN, int BN_>
+// The epilogue flavour is a template parameter: with a run-time switch the compiler kept a branch per group of four
+// columns and could not interleave the groups (12 instructions and ~60 cycles per element at two warps per scheduler;
+// 1.0 us of the 2.3 us epilogue).
+template <int A_MN, int B_MN, int BN_, int EPI_>
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmArgs args) {
-  gemm_tc_body<A_MN, B_MN, BN_>(args, blockIdx.x, blockIdx.y, blockIdx.z);
+  gemm_tc_body<A_MN, B_MN, BN_, EPI_>(args, blockIdx.x, blockIdx.y, blockIdx.z);
 }
 
-// host-side dispatch over the template instances
+// host-side dispatch over the template instances: forward layers are K-major x K-major, dX is K-major x MN-major,
+// raw outputs (weight gradients, input diffs, the unit test) exist for every operand layout
 typedef void (*TcKernel)(const GemmArgs);
-inline TcKernel tc_kernel_for(int a_mn, int b_mn, int bn) {
-  if (bn == 128) {
-    if (!a_mn && !b_mn) return gemm_tc_kernel<0, 0, 128>;
-    if (!a_mn && b_mn) return gemm_tc_kernel<0, 1, 128>;
-    if (a_mn && !b_mn) return gemm_tc_kernel<1, 0, 128>;
-    return gemm_tc_kernel<1, 1, 128>;
-  }
-  if (!a_mn && !b_mn) return gemm_tc_kernel<0, 0, 64>;
-  if (!a_mn && b_mn) return gemm_tc_kernel<0, 1, 64>;
-  if (a_mn && !b_mn) return gemm_tc_kernel<1, 0, 64>;
-  return gemm_tc_kernel<1, 1, 64>;
+template <int BN_>
+inline TcKernel tc_kernel_for_bn(int a_mn, int b_mn, int epi) {
+  if (epi == EPI_FWD) return (!a_mn && !b_mn) ? gemm_tc_kernel<0, 0, BN_, EPI_FWD> : nullptr;
+  if (epi == EPI_DX) return (!a_mn && b_mn) ? gemm_tc_kernel<0, 1, BN_, EPI_DX> : nullptr;
+  if (!a_mn && !b_mn) return gemm_tc_kernel<0, 0, BN_, EPI_PLAIN>;
+  if (!a_mn && b_mn) return gemm_tc_kernel<0, 1, BN_, EPI_PLAIN>;
+  if (a_mn && !b_mn) return gemm_tc_kernel<1, 0, BN_, EPI_PLAIN>;
+  return gemm_tc_kernel<1, 1, BN_, EPI_PLAIN>;
+}
+inline TcKernel tc_kernel_for(int a_mn, int b_mn, int bn, int epi) {
+  return bn == 128 ? tc_kernel_for_bn<128>(a_mn, b_mn, epi) : tc_kernel_for_bn<64>(a_mn, b_mn, epi);
 }
 inline int tc_max_stages(int bn) { return bn == 128 ? TcCfg<128>::MAX_STAGES : TcCfg<64>::MAX_STAGES; }
 inline int tc_smem_for(int bn, int stages) { return bn == 128 ? TcCfg<128>::smem_bytes(stages) : TcCfg<64>::smem_bytes(stages); }
@@ -675,11 +686,14 @@ inline cudaError_t tc_prepare(const void *fn, int bn) {
 }
 inline cudaError_t tc_prepare_all() {
   for (int bn : {64, 128})
-    for (int a = 0; a < 2; ++a)
-      for (int b = 0; b < 2; ++b) {
-        cudaError_t e = tc_prepare((const void *)tc_kernel_for(a, b, bn), bn);
-        if (e != cudaSuccess) return e;
-      }
+    for (int epi : {EPI_FWD, EPI_DX, EPI_PLAIN})
+      for (int a = 0; a < 2; ++a)
+        for (int b = 0; b < 2; ++b) {
+          TcKernel k = tc_kernel_for(a, b, bn, epi);
+          if (!k) continue;
+          cudaError_t e = tc_prepare((const void *)k, bn);
+          if (e != cudaSuccess) return e;
+        }
   return cudaSuccess;
 }
 

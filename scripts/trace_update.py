@@ -51,7 +51,8 @@ for i in range(len(t)):
     if name == "GEMM":
         gx, gy, gz, kb = (meta >> 16) & 0xfff, (meta >> 28) & 0xfff, (meta >> 40) & 0xff, (meta >> 48) & 0xfff
         print(f"{i:3d} {name:16s} {br} ({gx:2d},{gy:2d},{gz:2d}) {kb:3d} | {us(t[i,0]):7.1f} {us(t[i,2]):6.1f}({us(t[i,1]):6.1f}) "
-              f"{us(t[i,3]):6.1f}({us(t[i,8]):6.1f}) {us(t[i,4]):6.1f}({us(t[i,9]):6.1f}) {us(t[i,5]):6.1f}({us(t[i,10]):6.1f}) {us(t[i,6]):8.1f} | {us(t[i,6]) - us(t[i,2]):6.1f}")
+              f"{us(t[i,3]):6.1f}({us(t[i,8]):6.1f}) {us(t[i,4]):6.1f}({us(t[i,9]):6.1f}) {us(t[i,5]):6.1f}({us(t[i,10]):6.1f}) {us(t[i,6]):8.1f} | {us(t[i,6]) - us(t[i,2]):6.1f}"
+              f" | epi: acc+{us(t[i,11]) - us(t[i,4]):4.2f} staged+{us(t[i,12]) - us(t[i,11]):4.2f} stored+{us(t[i,5]) - us(t[i,12]):4.2f} synced+{us(t[i,13]) - us(t[i,5]):4.2f}")
     else:
         print(f"{i:3d} {name:16s} {br}                  | {'':7s} {us(t[i,0]):6.1f}({us(t[i,1]):6.1f}) {'':14s} {'':14s} {'':14s} {us(t[i,2]):8.1f} | "
               f"{us(t[i,2]) - us(t[i,0]):6.1f}")
