@@ -395,6 +395,8 @@ struct Tuning {
   int bn_big;       // 128: dX / dW GEMMs that fill the machine with 128x64 tiles anyway use 128x128 tiles (half the CTAs,
                     //      1.6x the tensor rate per CTA), so the two big GEMMs of a backward pass run side by side
   int bn_fwd, bn_fwd_side, bn_dx, bn_dw;   // N tile (64 / 128) per GEMM class
+  int bn32_max_tiles;   // forward / dX GEMMs with at most this many 128x64 output tiles use 128x32 tiles instead
+  int bn32_cluster;     // 1: such GEMMs may still split K over a 2-CTA cluster
   int dw_after_dx;  // bit l: the weight-gradient GEMM of tower layer l waits for the end of the dX chain (dZ[0])
   int bn_side_l1;   // N tile of a side chain's first layer: 128 halves its CTA count (128 -> 64), so that it fits beside
                     // the critical chain's second layer (64 CTAs) instead of queueing in front of it
@@ -412,6 +414,8 @@ struct Tuning {
     bn_big = env_int("DQNB_BN_BIG", 64);
     bn_fwd = env_int("DQNB_BN_FWD", 64);
     bn_fwd_side = env_int("DQNB_BN_FWD_SIDE", 64);
+    bn32_max_tiles = env_int("DQNB_BN32_MAX_TILES", 32);
+    bn32_cluster = env_int("DQNB_BN32_CLUSTER", 0);
     dw_after_dx = env_int("DQNB_DW_AFTER_DX", 0);
     bn_side_l1 = env_int("DQNB_BN_SIDE_L1", 128);
     bn_dx = env_int("DQNB_BN_DX", 64);
@@ -443,7 +447,13 @@ static int finish_gemm(const dqnb_config &cfg, Op *op) {
   if (cfg.gemm_mode == DQNB_GEMM_TCGEN05_3XTF32) {
     // A
     const int a_rows = p.a_mn ? p.K : p.M, b_rows = p.b_mn ? p.K : p.N;
-    if (p.bn != 64 && p.bn != 128) p.bn = 64;
+    if (p.bn != 32 && p.bn != 64 && p.bn != 128) p.bn = 64;
+    // Layers with few output tiles (the narrow top of a tower and the dX GEMMs that feed it) run on 128x32 tiles:
+    // twice the CTAs, each with a shorter mainloop per k-block (the A operand dominates the shared-memory reads) and
+    // half the bytes to push through its SM's ~40 B/clk store path in the epilogue.
+    bool narrow = false;
+    if (p.epi != EPI_PLAIN && p.bn == 64 && p.N % 32 == 0 &&
+        ((p.M + BM - 1) / BM) * ((p.N + 63) / 64) <= tuning().bn32_max_tiles) { p.bn = 32; narrow = true; }
     if (p.stages < 2 || p.stages > tc_max_stages(p.bn)) p.stages = tc_max_stages(p.bn);
     p.pdl_early = tuning().pdl_early;
     p.store_wait_full = tuning().store_wait_full;
@@ -453,6 +463,7 @@ static int finish_gemm(const dqnb_config &cfg, Op *op) {
     {
       const int tiles = ((p.M + BM - 1) / BM) * ((p.N + p.bn - 1) / p.bn);
       if (p.epi != EPI_PLAIN && p.splits == 1 && p.K / BK >= 16 && 2 * tiles <= 148 && cfg.use_graph >= 0 &&
+          (!narrow || tuning().bn32_cluster) &&
           !getenv("DQNB_NO_CLUSTER_SPLITK")) {
         p.cluster_k = 1;
         p.splits = 2;
@@ -2039,7 +2050,7 @@ int dqnb_gemm_test(int device, int gemm_mode, int a_mn, int b_mn, int M, int N, 
   Op op;
   GemmParams &p = op.gemm.p;
   memset(&p, 0, sizeof(p));
-  p.dbg = dbg & 3;
+  p.dbg = dbg & 7;
   p.stages = (dbg >> 4) & 0xf;           // 0: deepest ring that fits
   p.bn = (dbg >> 8) ? (dbg >> 8) : 64;
   p.dbg_clk = dclk;

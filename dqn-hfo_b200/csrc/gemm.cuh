@@ -45,7 +45,7 @@ struct GemmParams {
   // colsum_out[m_tile * colsum_stride + n]; reduce_kernel sums the m_tile planes in fixed order (nullable).
   float *colsum_out; long long colsum_stride;
   int apply_lrelu;                            // EPI_FWD: 0 for linear layers
-  int bn;                                     // N tile of the tcgen05 kernel: 64 or 128
+  int bn;                                     // N tile of the tcgen05 kernel: 32, 64 or 128
   int stages;                                 // depth of the TMA->MMA smem ring (2..4).  BN=64 with 2 stages is 98 KB
                                               // per CTA: two CTAs share an SM, one's epilogue under the other's mainloop
   int cluster_k;                              // 1: launched as 2-CTA clusters along z; the CTAs split K and the
@@ -188,7 +188,8 @@ struct TcCfg {
   static constexpr int MAX_STAGES = (TC_SMEM_MAX - 2048) / STAGE_BYTES > 4 ? 4 : (TC_SMEM_MAX - 2048) / STAGE_BYTES;
   static constexpr int MIN_STAGES = 2;          // also holds the epilogue's staging boxes (4 warps x BN/32 x 8 KB)
   static constexpr int smem_bytes(int stages) { return stages * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 512 /*bias tile*/ + 4 * BN_ * 4 /*column sums*/; }
-  static constexpr int TMEM_COLS = 2 * BN_;                    // two fp32 accumulators of BN columns
+  static constexpr int TMEM_USED = 3 * BN_;                    // three fp32 accumulators of BN columns: hi*hi, hi*lo, lo*hi
+  static constexpr int TMEM_COLS = TMEM_USED <= 128 ? 128 : TMEM_USED <= 256 ? 256 : 512;
 };
 constexpr int MN_GROUP_BYTES = 2 * 32 * BK * 4;       // MN-major: one 32-wide group, hi plane then lo plane
 
@@ -290,6 +291,22 @@ template <int MN>
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   return ((uint64_t)DescHi<MN>::hi << 32) | (uint64_t)(((saddr & 0x3FFFFu) >> 4) | DescHi<MN>::lbo);
 }
+// The B tile read as ONE operand of 2 BN columns, [B_hi | B_lo]:
+//  K-major  : the lo plane's rows follow the hi plane's rows (plane = BN rows of 128 B) - same descriptor, N doubled;
+//             accumulator columns [0, BN) = A*B_hi, [BN, 2 BN) = A*B_lo.
+//  MN-major : every 32-wide group holds its hi plane (4 KB) then its lo plane (4 KB); with LBO = 4 KB the operand's
+//             32-column groups are hi0, lo0, hi1, lo1, ..: accumulator columns 64 g + [0, 32) = A*B_hi of group g,
+//             64 g + [32, 64) = A*B_lo of group g.
+template <int MN>
+__device__ __forceinline__ uint64_t make_desc_bcat(uint32_t saddr) {
+  constexpr uint32_t lbo = MN ? ((4096u >> 4) << 16) : (1u << 16);
+  return ((uint64_t)DescHi<MN>::hi << 32) | (uint64_t)(((saddr & 0x3FFFFu) >> 4) | lbo);
+}
+// TMEM column of the 32-column chunk ci of accumulator hh (hi*hi), hl (A_hi*B_lo), lh (A_lo*B_hi)
+template <int B_MN, int BN_> __device__ __forceinline__ uint32_t acc_col_hh(int ci) { return B_MN ? 64u * ci : 32u * ci; }
+template <int B_MN, int BN_> __device__ __forceinline__ uint32_t acc_col_hl(int ci) { return B_MN ? 64u * ci + 32u : (uint32_t)BN_ + 32u * ci; }
+template <int B_MN, int BN_> __device__ __forceinline__ uint32_t acc_col_lh(int ci) { return 2u * BN_ + 32u * ci; }
+
 // instruction descriptor: D=f32 [4,6)=1, A=tf32 [7,10)=2, B=tf32 [10,13)=2, a_major [15], b_major [16],
 // N>>3 [17,23), M>>4 [24,29)
 __host__ __device__ constexpr uint32_t umma_idesc_tf32(int a_mn, int b_mn, int n) {
@@ -417,8 +434,8 @@ __device__ __forceinline__ void gemm_tc_body(const GemmArgs &args, const int n_t
   } else if (warp == 1) {
     // ---------------- MMA issuer ----------------
     constexpr uint32_t idesc = umma_idesc_tf32(A_MN, B_MN, BN_);
+    constexpr uint32_t idesc_w = umma_idesc_tf32(A_MN, B_MN, 2 * BN_);
     constexpr uint32_t a_lo_off = A_MN ? 4096u : (uint32_t)Cfg::A_PLANE_BYTES;
-    constexpr uint32_t b_lo_off = B_MN ? 4096u : (uint32_t)Cfg::B_PLANE_BYTES;
     int s = 0;
     uint32_t ph = 0;
     for (int it = 0; it < iters; ++it) {
@@ -428,20 +445,22 @@ __device__ __forceinline__ void gemm_tc_body(const GemmArgs &args, const int n_t
       if (it == 0 && lane == 0) { DQNB_STAMP(3); DQNB_STAMP_MAX(8); }
       const uint32_t sa = base + s * Cfg::STAGE_BYTES, sb = sa + Cfg::A_STAGE_BYTES;
       const uint64_t a_hi = make_desc<A_MN>(sa), a_lo = make_desc<A_MN>(sa + a_lo_off);
-      const uint64_t b_hi = make_desc<B_MN>(sb), b_lo = make_desc<B_MN>(sb + b_lo_off);
+      const uint64_t b_hi = make_desc<B_MN>(sb), b_cat = make_desc_bcat<B_MN>(sb);
       if (elect_one()) {
         if (!(p.dbg & 1)) {
 #pragma unroll
           for (int ks = 0; ks < BK / 8; ++ks) {
             const uint64_t ka = (uint64_t)(ks * DescHi<A_MN>::kstep), kb = (uint64_t)(ks * DescHi<B_MN>::kstep);
-            // Two TMEM accumulators: the dominant hi*hi chain and the small cross terms.  The tensor
-            // core truncates when it adds into the fp32 accumulator, so keeping the 2^-11-scaled
-            // terms out of the long chain cuts the accumulated rounding bias ~3x; the epilogue adds
-            // the two.
+            // Two instructions per k-step instead of three: a tcgen05.mma costs ~60 cycles + 0.2 per column of N
+            // here (measured, operands in shared memory: 67 / 73 / 87 cycles at N = 32 / 64 / 128), so A_hi is
+            // multiplied with B_hi and B_lo in ONE instruction of N = 2 BN - the two planes of the B tile are
+            // neighbours in shared memory and read as one operand - and A_lo with B_hi in a second one.
+            // Three TMEM accumulators: the dominant hi*hi chain and the two small cross terms.  The tensor core
+            // truncates when it adds into the fp32 accumulator, so keeping the 2^-11-scaled terms out of the long
+            // chain cuts the accumulated rounding bias ~3x; the epilogue adds them.
             const uint32_t first = (it > 0 || ks > 0) ? 1u : 0u;
-            tc_mma_tf32(tmem, a_hi + ka, b_hi + kb, idesc, first);
-            tc_mma_tf32(tmem + BN_, a_lo + ka, b_hi + kb, idesc, first);
-            tc_mma_tf32(tmem + BN_, a_hi + ka, b_lo + kb, idesc, 1u);
+            tc_mma_tf32(tmem, a_hi + ka, b_cat + kb, idesc_w, first);
+            tc_mma_tf32(tmem + 2 * BN_, a_lo + ka, b_hi + kb, idesc, first);
           }
         }
         tc_commit(empty);                  // frees the smem stage when these MMAs retire
@@ -467,8 +486,10 @@ __device__ __forceinline__ void gemm_tc_body(const GemmArgs &args, const int n_t
     // for coalesced stores: 2.5 us.)
     constexpr int LDS = BN_ + 4;             // row stride of the split-K peer's raw partial tile
     constexpr int NCH = BN_ / 32;            // 32-column chunks of the tile
-    constexpr int MYCH = NCH / 2;            // ... handled by this warp: chunks half, half + 2, ..
-    static_assert(BN_ == 64 || BN_ == 128, "epilogue mapping assumes BN of 64 or 128");
+    constexpr int MYCH = (NCH + 1) / 2;      // ... handled by this warp: chunks half, half + 2, .. (those below NCH)
+    static_assert(BN_ == 32 || BN_ == 64 || BN_ == 128, "epilogue mapping assumes BN of 32, 64 or 128");
+    // BN = 32 (layers with few output tiles: twice the CTAs, half the bytes each SM has to store): one chunk per TMEM
+    // lane quarter, taken by warps 0-3; warps 4-7 only help with the bias tile
     static_assert(BM * LDS * 4 <= Cfg::MIN_STAGES * Cfg::STAGE_BYTES, "peer partial tile must fit in the stage ring");
     static_assert(4 * NCH * 2 * 4096 <= Cfg::MIN_STAGES * Cfg::STAGE_BYTES, "staging boxes must fit in the stage ring");
     const int q = warp & 3;                  // TMEM lane quarter this warp may read
@@ -492,7 +513,7 @@ __device__ __forceinline__ void gemm_tc_body(const GemmArgs &args, const int n_t
     for (int i = 0; i < MYCH; ++i) {
       const int c0 = (half + 2 * i) * 32;
       rbits[i] = 0u;
-      if (!peer && EPI_ == EPI_DX && m_row < p.M && n_base + c0 < p.N)
+      if (!peer && EPI_ == EPI_DX && half + 2 * i < NCH && m_row < p.M && n_base + c0 < p.N)
         rbits[i] = __ldg(p.relu_bits_in + (long long)m_row * p.ldbits + ((n_base + c0) >> 5));
     }
     asm volatile("bar.sync 1, %0;" ::"n"(TC_THREADS) : "memory");   // bias tile visible; warps 0/1 are done issuing
@@ -508,25 +529,33 @@ __device__ __forceinline__ void gemm_tc_body(const GemmArgs &args, const int n_t
 #pragma unroll
       for (int i = 0; i < MYCH; ++i) {
         const int c0 = (half + 2 * i) * 32;
-        uint32_t r[32], r2[32];
+        if (half + 2 * i >= NCH) break;
+        uint32_t r[32], r2[32], r3[32];
         if (iters > 0) {
-          tmem_ld32(taddr0 + (uint32_t)c0, r);
-          tmem_ld32(taddr0 + (uint32_t)c0 + BN_, r2);
+          tmem_ld32(taddr0 + acc_col_hh<B_MN, BN_>(half + 2 * i), r);
+          tmem_ld32(taddr0 + acc_col_hl<B_MN, BN_>(half + 2 * i), r2);
+          tmem_ld32(taddr0 + acc_col_lh<B_MN, BN_>(half + 2 * i), r3);
           tmem_wait_ld();
         } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) { r[j] = 0u; r2[j] = 0u; }
+          for (int j = 0; j < 32; ++j) { r[j] = 0u; r2[j] = 0u; r3[j] = 0u; }
         }
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + (__uint_as_float(r2[j]) + __uint_as_float(r3[j]));
 #pragma unroll
         for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<float4 *>(mine + c0 + j) =
-              make_float4(__uint_as_float(r[j]) + __uint_as_float(r2[j]), __uint_as_float(r[j + 1]) + __uint_as_float(r2[j + 1]),
-                          __uint_as_float(r[j + 2]) + __uint_as_float(r2[j + 2]), __uint_as_float(r[j + 3]) + __uint_as_float(r2[j + 3]));
+          *reinterpret_cast<float4 *>(mine + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
       }
     } else {
       // the TMEM loads of this warp's first chunk go out before the (cluster) hand-shake
-      uint32_t ra[2][32], rb[2][32];
-      if (iters > 0) { tmem_ld32(taddr0 + (uint32_t)(half * 32), ra[0]); tmem_ld32(taddr0 + (uint32_t)(half * 32) + BN_, rb[0]); }
+      uint32_t ra[32], rb[32], rc[32];
+      auto load_chunk = [&](int ci) {
+        tmem_ld32(taddr0 + acc_col_hh<B_MN, BN_>(ci), ra);
+        tmem_ld32(taddr0 + acc_col_hl<B_MN, BN_>(ci), rb);
+        tmem_ld32(taddr0 + acc_col_lh<B_MN, BN_>(ci), rc);
+      };
+      if (iters > 0 && half < NCH) load_chunk(half);
       if (clus) { cluster_arrive_release(); cluster_wait_acquire(); }   // barrier #1: the peer's partial is visible
       if (warp == 2 && lane == 0) { DQNB_STAMP(4); DQNB_STAMP_MAX(9); }
       const float *peer_row = st_hi + lane * LDS;          // same offset inside the peer CTA's shared memory
@@ -536,19 +565,16 @@ __device__ __forceinline__ void gemm_tc_body(const GemmArgs &args, const int n_t
 #pragma unroll
       for (int i = 0; i < MYCH; ++i) {
         const int c0 = (half + 2 * i) * 32;
-        const int cur = i & 1;
+        if (half + 2 * i >= NCH) break;
         float v[32];
         const uint32_t bits_in = rbits[i];
         uint32_t bits_out = 0u;
         if (iters > 0) {
           tmem_wait_ld();
           if (i == 0 && warp == 2 && lane == 0) DQNB_STAMP(11);       // first accumulator chunk in registers
-          if (i + 1 < MYCH) {              // next chunk in flight while this one is processed
-            tmem_ld32(taddr0 + (uint32_t)(c0 + 64), ra[cur ^ 1]);
-            tmem_ld32(taddr0 + (uint32_t)(c0 + 64) + BN_, rb[cur ^ 1]);
-          }
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(ra[cur][j]) + __uint_as_float(rb[cur][j]);
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(ra[j]) + (__uint_as_float(rb[j]) + __uint_as_float(rc[j]));
+          if (i + 1 < MYCH && half + 2 * (i + 1) < NCH) load_chunk(half + 2 * (i + 1));   // next chunk in flight while this one is processed
         } else {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = 0.f;
@@ -616,7 +642,7 @@ __device__ __forceinline__ void gemm_tc_body(const GemmArgs &args, const int n_t
         // hand this chunk's box (both planes) to the TMA unit; the next chunk is staged meanwhile
         fence_proxy_async_smem();
         __syncwarp();
-        if (i == MYCH - 1 && warp == 2 && lane == 0) DQNB_STAMP(12);  // last box staged
+        if (half + 2 * (i + 1) >= NCH && warp == 2 && lane == 0) DQNB_STAMP(12);  // last box staged
         if (lane == 0 && n_base + c0 < p.N && m_tile * BM + q * 32 < p.M) {
           tma_store_3d(&args.tmD, box - row_off, n_base + c0, m_tile * BM + q * 32, planes_out == 1 ? split : 0);
           bulk_commit();
@@ -674,10 +700,12 @@ inline TcKernel tc_kernel_for_bn(int a_mn, int b_mn, int epi) {
   return gemm_tc_kernel<1, 1, BN_, EPI_PLAIN>;
 }
 inline TcKernel tc_kernel_for(int a_mn, int b_mn, int bn, int epi) {
-  return bn == 128 ? tc_kernel_for_bn<128>(a_mn, b_mn, epi) : tc_kernel_for_bn<64>(a_mn, b_mn, epi);
+  return bn == 128 ? tc_kernel_for_bn<128>(a_mn, b_mn, epi) : bn == 32 ? tc_kernel_for_bn<32>(a_mn, b_mn, epi) : tc_kernel_for_bn<64>(a_mn, b_mn, epi);
 }
-inline int tc_max_stages(int bn) { return bn == 128 ? TcCfg<128>::MAX_STAGES : TcCfg<64>::MAX_STAGES; }
-inline int tc_smem_for(int bn, int stages) { return bn == 128 ? TcCfg<128>::smem_bytes(stages) : TcCfg<64>::smem_bytes(stages); }
+inline int tc_max_stages(int bn) { return bn == 128 ? TcCfg<128>::MAX_STAGES : bn == 32 ? TcCfg<32>::MAX_STAGES : TcCfg<64>::MAX_STAGES; }
+inline int tc_smem_for(int bn, int stages) {
+  return bn == 128 ? TcCfg<128>::smem_bytes(stages) : bn == 32 ? TcCfg<32>::smem_bytes(stages) : TcCfg<64>::smem_bytes(stages);
+}
 inline cudaError_t tc_prepare(const void *fn, int bn) {
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_for(bn, tc_max_stages(bn)));
   if (e != cudaSuccess) return e;
@@ -685,7 +713,7 @@ inline cudaError_t tc_prepare(const void *fn, int bn) {
   return cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 inline cudaError_t tc_prepare_all() {
-  for (int bn : {64, 128})
+  for (int bn : {32, 64, 128})
     for (int epi : {EPI_FWD, EPI_DX, EPI_PLAIN})
       for (int a = 0; a < 2; ++a)
         for (int b = 0; b < 2; ++b) {

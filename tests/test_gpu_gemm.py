@@ -39,7 +39,7 @@ def test_gemm_matches_float64(mode, a_mn, b_mn, M, N, K, splits):
     assert relerr(Cm, ref) < tol, (relerr(Cm, ref), ms)
 
 
-@pytest.mark.parametrize("bn,stages", [(128, 0), (128, 2), (64, 2), (64, 3)])
+@pytest.mark.parametrize("bn,stages", [(128, 0), (128, 2), (64, 2), (64, 3), (32, 0), (32, 2)])
 @pytest.mark.parametrize("a_mn,b_mn,M,N,K,splits", [(0, 0, 1024, 512, 1024, 1), (0, 1, 1024, 1024, 512, 1), (1, 1, 512, 1024, 1024, 2),
                                                     (1, 1, 64, 128, 256, 4), (0, 0, 256, 192, 96, 1)])
 def test_gemm_tile_and_ring_variants(bn, stages, a_mn, b_mn, M, N, K, splits):
