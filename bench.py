@@ -438,10 +438,17 @@ def main():
                 line["wide_mlp"]["gemm_error"] = str(e)
         barrier()
         dw.close()
+        # every rank runs the act-path leg: with N > 1 the updates in flight exchange gradients, so all ranks must
+        # enqueue them (a lone rank would wait for its peers until the exchange times out)
+        barrier()
+        act_idle = act_latency(d, s)
+        barrier()
+        act_busy = act_latency(d, s, busy_updates=300)
+        barrier()
         if rank == 0:
             line["act_path"] = {
                 "unit": "us per dqnb_select_actions call (host rows in, host rows out; median of 200)",
-                "rows": [1, 8, 64], "idle": act_latency(d, s), "while_updating": act_latency(d, s, busy_updates=300),
+                "rows": [1, 8, 64], "idle": act_idle, "while_updating": act_busy,
                 "what": "skinny-M kernels on the act stream reading the actor snapshot; never waits for the learner's stream",
             }
             try:

@@ -67,6 +67,7 @@ def lib():
     L.dqnb_get_params.argtypes = [H, C.c_int, fp]
     L.dqnb_init_params.argtypes = [H, C.c_uint64, C.c_float]
     L.dqnb_clone_targets.argtypes = [H]
+    L.dqnb_copy_shared_layers.argtypes = [H, H, C.c_int32, C.c_int32]
     L.dqnb_set_opt_state.argtypes = [H, C.c_int, fp, fp, C.c_int32]
     L.dqnb_get_opt_state.argtypes = [H, C.c_int, fp, fp, ip]
     L.dqnb_iters.argtypes = [H, ip, ip]
@@ -103,7 +104,7 @@ def lib():
 
 EXPORTS = [
     "dqnb_default_config", "dqnb_last_error", "dqnb_version", "dqnb_create", "dqnb_destroy",
-    "dqnb_param_count", "dqnb_set_params", "dqnb_get_params", "dqnb_init_params", "dqnb_clone_targets",
+    "dqnb_param_count", "dqnb_set_params", "dqnb_get_params", "dqnb_init_params", "dqnb_clone_targets", "dqnb_copy_shared_layers",
     "dqnb_set_opt_state", "dqnb_get_opt_state", "dqnb_iters", "dqnb_add_transitions",
     "dqnb_add_transition", "dqnb_memory_size", "dqnb_clear_memory", "dqnb_get_transitions",
     "dqnb_update", "dqnb_update_async", "dqnb_results", "dqnb_update_with_indices", "dqnb_benchmark", "dqnb_benchmark_gemms",
@@ -200,6 +201,10 @@ class DQNB:
 
     def clone_targets(self):
         _check(lib().dqnb_clone_targets(self._h))
+
+    def copy_shared_layers_from(self, src, n_actor_layers, n_critic_layers):
+        """ShareParameters write-through: the first n layers (and their target-net twins) of `src` overwrite ours."""
+        _check(lib().dqnb_copy_shared_layers(self._h, src._h, n_actor_layers, n_critic_layers))
 
     def set_opt_state(self, net, m, v, it):
         m = np.ascontiguousarray(m, np.float32)

@@ -395,6 +395,7 @@ struct Tuning {
   int bn_big;       // 128: dX / dW GEMMs that fill the machine with 128x64 tiles anyway use 128x128 tiles (half the CTAs,
                     //      1.6x the tensor rate per CTA), so the two big GEMMs of a backward pass run side by side
   int bn_fwd, bn_fwd_side, bn_dx, bn_dw;   // N tile (64 / 128) per GEMM class
+  int ts_min_kb;        // forward / dX GEMMs with at least this many k-blocks per CTA run in A-in-TMEM mode (0 < x; 9999 = never)
   int bn32_max_tiles;   // forward / dX GEMMs with at most this many 128x64 output tiles use 128x32 tiles instead
   int bn32_cluster;     // 1: such GEMMs may still split K over a 2-CTA cluster
   int dw_after_dx;  // bit l: the weight-gradient GEMM of tower layer l waits for the end of the dX chain (dZ[0])
@@ -414,6 +415,7 @@ struct Tuning {
     bn_big = env_int("DQNB_BN_BIG", 64);
     bn_fwd = env_int("DQNB_BN_FWD", 64);
     bn_fwd_side = env_int("DQNB_BN_FWD_SIDE", 64);
+    ts_min_kb = env_int("DQNB_TS_MIN_KB", 8);
     bn32_max_tiles = env_int("DQNB_BN32_MAX_TILES", 32);
     bn32_cluster = env_int("DQNB_BN32_CLUSTER", 0);
     dw_after_dx = env_int("DQNB_DW_AFTER_DX", 0);
@@ -469,6 +471,8 @@ static int finish_gemm(const dqnb_config &cfg, Op *op) {
         p.splits = 2;
       }
     }
+    // long enough K-major-A mainloops read A from tensor memory (four mover warps copy it there, gemm.cuh)
+    p.a_ts = (!p.a_mn && p.epi != EPI_PLAIN && (p.K / BK) / p.splits >= tuning().ts_min_kb) ? 1 : 0;
     if (make_tmap(&op->gemm.tmA, p.A, a_rows, p.lda, p.a_plane, p.a_mn ? 32 : BM, p.a_mn != 0)) return -1;
     if (make_tmap(&op->gemm.tmB, p.B, b_rows, p.ldb, p.b_plane, p.b_mn ? 32 : p.bn, p.b_mn != 0)) return -1;
     if (p.epi == EPI_PLAIN) {
@@ -1325,6 +1329,57 @@ int dqnb_set_params(dqnb_handle h, int net, const float *params) {
   return 0;
 }
 
+// Multi-agent parameter sharing (dqn.cpp:1048-1079 ShareParameters -> ShareLayer -> Blob::ShareData): the first
+// n layers-with-parameters (Caffe layer order: tower layers, then the head layers) of src's actor / critic and of their
+// target nets become dst's.  Two handles cannot alias sub-ranges of each other's flat buffers, so the host mirror calls
+// this after every update of a sharing group (write-through): what a member reads at its next update or act call is
+// what Blob::ShareData would have shown it.
+static void shared_ranges(const NetGeom &g, int n_layers, std::vector<std::pair<long long, long long>> &out) {
+  int i = 0;
+  for (; i < g.n_hidden && i < n_layers; ++i) {
+    out.push_back({g.L[i].w_off, (long long)g.L[i].Np * g.L[i].Kp});
+    out.push_back({g.L[i].b_off, (long long)g.L[i].Np});
+  }
+  if (i >= n_layers) return;
+  if (g.critic) {                                   // q_values_layer
+    out.push_back({g.hw_off, (long long)g.Hp}); out.push_back({g.hb_off, 1});
+    return;
+  }
+  out.push_back({g.hw_off, 4LL * g.Hp}); out.push_back({g.hb_off, 4});                       // action_layer
+  if (i + 1 < n_layers) { out.push_back({g.hw_off + 4LL * g.Hp, 6LL * g.Hp}); out.push_back({g.hb_off + 4, 6}); }   // actionpara_layer
+}
+static int sync_all(dqnb_handle h);
+int dqnb_copy_shared_layers(dqnb_handle dst, dqnb_handle src, int32_t n_actor_layers, int32_t n_critic_layers) {
+  if (!dst || !src || dst == src || n_actor_layers < 0 || n_critic_layers < 0) DQNB_FAIL("bad argument");
+  if (dst->gA.flat != src->gA.flat || dst->gC.flat != src->gC.flat || dst->cfg.n_hidden != src->cfg.n_hidden)
+    DQNB_FAIL("sharing needs identical net shapes");
+  if (n_actor_layers > src->gA.n_hidden + 2 || n_critic_layers > src->gC.n_hidden + 1) DQNB_FAIL("more layers to share than the net has");
+  if (sync_all(src) || sync_all(dst)) return -1;
+  DQNB_CUDA(cudaSetDevice(dst->cfg.device));
+  DQNB_CUDA(cudaStreamSynchronize(dst->astream));
+  for (int critic = 0; critic < 2; ++critic) {
+    const NetGeom &g = critic ? dst->gC : dst->gA;
+    std::vector<std::pair<long long, long long>> rs;
+    shared_ranges(g, critic ? n_critic_layers : n_actor_layers, rs);
+    for (int target = 0; target < 2; ++target) {
+      const int net = (critic ? DQNB_CRITIC : DQNB_ACTOR) + (target ? 2 : 0);
+      for (auto &r : rs)
+        for (int plane = 0; plane < 2; ++plane)
+          DQNB_CUDA(cudaMemcpyAsync(dst->P[net] + plane * g.flat + r.first, src->P[net] + plane * g.flat + r.first,
+                                    sizeof(float) * r.second, cudaMemcpyDefault, dst->stream));
+    }
+    if (!critic && dst->snapA)                      // dst's act path reads fp32 snapshots of its actor: refresh both
+      for (auto &r : rs)
+        for (int buf = 0; buf < 2; ++buf) {
+          join_kernel<<<(unsigned)((r.second + 255) / 256), 256, 0, dst->stream>>>(
+              dst->P[DQNB_ACTOR] + r.first, dst->P[DQNB_ACTOR] + g.flat + r.first, dst->snapA + buf * g.flat + r.first, r.second);
+          DQNB_CUDA(cudaGetLastError());
+        }
+  }
+  DQNB_CUDA(cudaStreamSynchronize(dst->stream));
+  return 0;
+}
+
 static int read_flat(dqnb_handle h, const NetGeom &g, const float *dev_hi, const float *dev_lo, float *caffe_out) {
   std::vector<float> a((size_t)g.flat), b;
   DQNB_CUDA(cudaStreamSynchronize(h->stream));
@@ -2059,6 +2114,7 @@ int dqnb_gemm_test(int device, int gemm_mode, int a_mn, int b_mn, int M, int N, 
   p.B = dBs; p.b_plane = (long long)nb; p.ldb = b_mn ? N : K;
   p.out = dP; p.out_split_stride = (long long)nc; p.ldo = N;
   if (finish_gemm(cfg, &op)) return -1;
+  p.a_ts = ((dbg & 4) && !a_mn) ? 1 : 0;   // unit test of the A-in-TMEM mainloop with the raw epilogue
   cudaEvent_t e0, e1;
   DQNB_CUDA(cudaEventCreate(&e0)); DQNB_CUDA(cudaEventCreate(&e1));
   const int reps = 20;

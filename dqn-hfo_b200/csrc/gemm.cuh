@@ -54,6 +54,8 @@ struct GemmParams {
                                               //    then sit on SMs - 197 KB of smem each - for this kernel's whole
                                               //    duration); 0: when the last MMA has been issued, so they only overlap
                                               //    the accumulator drain + epilogue (measured: profiles/r01c_*)
+  int a_ts;                                   // 1 (K-major A only): the A tile is copied shared -> tensor memory by four mover
+                                              // warps and tcgen05.mma reads it from there (see gemm_tc_body)
   int store_wait_full;                        // 1: the epilogue waits for its TMA stores to be written, not just read (A/B knob)
   int dbg;                                    // perf experiments (gemm_test only): bit0 skip MMA, bit1 skip TMA
   long long *dbg_clk;                         // optional: MMA-thread clock64 stamps {start, issued, complete}
@@ -188,6 +190,9 @@ struct TcCfg {
   static constexpr int MAX_STAGES = (TC_SMEM_MAX - 2048) / STAGE_BYTES > 4 ? 4 : (TC_SMEM_MAX - 2048) / STAGE_BYTES;
   static constexpr int MIN_STAGES = 2;          // also holds the epilogue's staging boxes (4 warps x BN/32 x 8 KB)
   static constexpr int smem_bytes(int stages) { return stages * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 512 /*bias tile*/ + 4 * BN_ * 4 /*column sums*/; }
+  // A-in-TMEM mode: ring of A tiles behind the accumulators, [stage][hi: 32 columns | lo: 32 columns] (one k-block)
+  static constexpr int A_TMEM_COL0 = 3 * BN_;
+  static constexpr int A_TMEM_STAGES = (512 - 3 * BN_) / 64 >= 4 ? 4 : (512 - 3 * BN_) / 64;
   static constexpr int TMEM_USED = 3 * BN_;                    // three fp32 accumulators of BN columns: hi*hi, hi*lo, lo*hi
   static constexpr int TMEM_COLS = TMEM_USED <= 128 ? 128 : TMEM_USED <= 256 ? 256 : 512;
 };
@@ -270,6 +275,34 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uin
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
       "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+
+// A operand read from tensor memory (lane = row, 8 columns of 32-bit per K = 8 step), B from shared memory
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc,
+                                               uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// registers -> tensor memory: thread t of the warp writes 32 consecutive columns of lane (taddr.lane + t)
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+        "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+        "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void ld_smem_u4(uint32_t addr, uint32_t &a, uint32_t &b, uint32_t &c, uint32_t &d) {
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr) : "memory");
 }
 
 // UMMA shared-memory matrix descriptor (sm_100): start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46)
@@ -360,7 +393,7 @@ __device__ __forceinline__ void gemm_tc_body(const GemmArgs &args, const int n_t
   uint8_t *base_ptr = smem_raw + (base - raw);
   const uint32_t bars = base + STAGES * Cfg::STAGE_BYTES;   // full[STAGES], empty[STAGES], tmem_full
   volatile uint32_t *tmem_slot =
-      reinterpret_cast<volatile uint32_t *>(base_ptr + STAGES * Cfg::STAGE_BYTES + 128);
+      reinterpret_cast<volatile uint32_t *>(base_ptr + STAGES * Cfg::STAGE_BYTES + 192);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kblocks = p.K / BK;
   const int per = (kblocks + p.splits - 1) / p.splits;
@@ -368,6 +401,11 @@ __device__ __forceinline__ void gemm_tc_body(const GemmArgs &args, const int n_t
   const int kb1 = min(kblocks, kb0 + per);
   const int iters = max(kb1 - kb0, 0);
   const uint32_t tfull = bars + 8 * (2 * STAGES);
+  // A-in-TMEM mode (K-major A): a_full[AT] "tile copied into tensor memory" (one arrival per mover warp),
+  // a_empty[AT] "the MMAs that read it have retired"
+  constexpr int AT = Cfg::A_TMEM_STAGES;
+  const bool a_ts = !A_MN && p.a_ts != 0;
+  const uint32_t afull0 = bars + 8 * (2 * STAGES + 1), aempty0 = afull0 + 8 * AT;
   const bool clus = p.cluster_k != 0;          // split-K over a 2-CTA cluster (blockIdx.z = cluster rank)
   uint32_t crank = 0;
   if (clus) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
@@ -378,12 +416,13 @@ __device__ __forceinline__ void gemm_tc_body(const GemmArgs &args, const int n_t
     asm volatile("prefetch.tensormap [%0];" ::"l"(&args.tmB) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&args.tmD) : "memory");
     for (int i = 0; i < 2 * STAGES + 1; ++i) mbar_init(bars + 8 * i, 1);
+    for (int i = 0; i < AT; ++i) { mbar_init(afull0 + 8 * i, 4); mbar_init(aempty0 + 8 * i, 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      smem_u32((const void *)tmem_slot)),
-                 "n"(Cfg::TMEM_COLS)
+                 "r"(a_ts ? 512u : (uint32_t)Cfg::TMEM_COLS)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -436,11 +475,12 @@ __device__ __forceinline__ void gemm_tc_body(const GemmArgs &args, const int n_t
     constexpr uint32_t idesc = umma_idesc_tf32(A_MN, B_MN, BN_);
     constexpr uint32_t idesc_w = umma_idesc_tf32(A_MN, B_MN, 2 * BN_);
     constexpr uint32_t a_lo_off = A_MN ? 4096u : (uint32_t)Cfg::A_PLANE_BYTES;
-    int s = 0;
-    uint32_t ph = 0;
+    int s = 0, as = 0;
+    uint32_t ph = 0, pa = 0;
     for (int it = 0; it < iters; ++it) {
       const uint32_t full = bars + 8 * s, empty = bars + 8 * (STAGES + s);
       mbar_wait(full, ph);
+      if (a_ts) mbar_wait(afull0 + 8 * as, pa);
       tc_fence_after();
       if (it == 0 && lane == 0) { DQNB_STAMP(3); DQNB_STAMP_MAX(8); }
       const uint32_t sa = base + s * Cfg::STAGE_BYTES, sb = sa + Cfg::A_STAGE_BYTES;
@@ -459,20 +499,62 @@ __device__ __forceinline__ void gemm_tc_body(const GemmArgs &args, const int n_t
             // truncates when it adds into the fp32 accumulator, so keeping the 2^-11-scaled terms out of the long
             // chain cuts the accumulated rounding bias ~3x; the epilogue adds them.
             const uint32_t first = (it > 0 || ks > 0) ? 1u : 0u;
-            tc_mma_tf32(tmem, a_hi + ka, b_cat + kb, idesc_w, first);
-            tc_mma_tf32(tmem + 2 * BN_, a_lo + ka, b_hi + kb, idesc, first);
+            if (a_ts) {
+              // A from tensor memory: no 4 KB shared-memory read of the A slice per instruction (measured: 74 / 53
+              // cycles at N = 128 / 64 instead of 87 / 73)
+              const uint32_t a_t = tmem + (uint32_t)Cfg::A_TMEM_COL0 + (uint32_t)as * 64u + (uint32_t)ks * 8u;
+              tc_mma_tf32_ts(tmem, a_t, b_cat + kb, idesc_w, first);
+              tc_mma_tf32_ts(tmem + 2 * BN_, a_t + 32u, b_hi + kb, idesc, first);
+            } else {
+              tc_mma_tf32(tmem, a_hi + ka, b_cat + kb, idesc_w, first);
+              tc_mma_tf32(tmem + 2 * BN_, a_lo + ka, b_hi + kb, idesc, first);
+            }
           }
         }
         tc_commit(empty);                  // frees the smem stage when these MMAs retire
+        if (a_ts) tc_commit(aempty0 + 8 * as);   // ... and the A tile in tensor memory
       }
       __syncwarp();
       if (++s == STAGES) { s = 0; ph ^= 1u; }
+      if (++as == AT) { as = 0; pa ^= 1u; }
     }
     if (elect_one()) {
       tc_commit(tfull);                    // accumulators complete -> epilogue
     }
     __syncwarp();
     if (!p.pdl_early) pdl_launch_dependents();   // every MMA is issued: the next kernel's prologue overlaps our tail
+  } else if (!A_MN && warp >= 4 && a_ts) {
+    // ---------------- A movers (A-in-TMEM mode): shared memory -> registers -> tensor memory ----------------
+    // Warp 4 + q owns TMEM lane quarter q = rows 32 q .. 32 q + 31 of the tile; a thread copies its row of the
+    // k-block: 128 B of the hi plane and 128 B of the lo plane (16-byte chunk j of row r sits at j ^ (r & 7):
+    // conflict-free LDS.128) into 32 + 32 columns of the stage's slot.
+    const int q = warp & 3;
+    const uint32_t row = (uint32_t)(q * 32 + lane);
+    const uint32_t row_off = row * 128u, sw = row & 7u;
+    const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)Cfg::A_TMEM_COL0;
+    int s = 0, as = 0;
+    uint32_t ph = 0, pa = 0;
+    for (int it = 0; it < iters; ++it) {
+      mbar_wait(aempty0 + 8 * as, pa ^ 1u);
+      mbar_wait(bars + 8 * s, ph);
+      const uint32_t sa = base + s * Cfg::STAGE_BYTES + row_off;
+      uint32_t rh[32], rl[32];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t o = ((uint32_t)j ^ sw) << 4;
+        ld_smem_u4(sa + o, rh[4 * j], rh[4 * j + 1], rh[4 * j + 2], rh[4 * j + 3]);
+        ld_smem_u4(sa + (uint32_t)Cfg::A_PLANE_BYTES + o, rl[4 * j], rl[4 * j + 1], rl[4 * j + 2], rl[4 * j + 3]);
+      }
+      tc_fence_after();                    // the slot's previous readers (MMAs) retired: ordered before our writes
+      tmem_st32(t_lane + (uint32_t)as * 64u, rh);
+      tmem_st32(t_lane + (uint32_t)as * 64u + 32u, rl);
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(afull0 + 8 * as);
+      if (++s == STAGES) { s = 0; ph ^= 1u; }
+      if (++as == AT) { as = 0; pa ^= 1u; }
+    }
   }
   {
     // ---------------- epilogue: TMEM -> registers -> swizzled smem -> TMA store ----------------
@@ -674,7 +756,7 @@ __device__ __forceinline__ void gemm_tc_body(const GemmArgs &args, const int n_t
   if (p.dbg_clk && threadIdx.x == 0) atomicMax(p.dbg_clk + 6, (long long)gtime_ns());   // latest CTA exit of the grid
   if (warp == 1) {
     __syncwarp();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(Cfg::TMEM_COLS)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(a_ts ? 512u : (uint32_t)Cfg::TMEM_COLS)
                  : "memory");
   }
 }

@@ -750,6 +750,9 @@ __global__ void __launch_bounds__(512) p2p_allreduce_kernel(const P2PArgs a) {
   trace_begin(a.trace);
   __shared__ int s_last;
   const int W = a.world;
+  // a peer already missed its timeout (sticky, set before this launch): the replicas have stopped updating
+  // (adam_kernel skips), so later exchanges return at once instead of waiting out the timeout again
+  if (*reinterpret_cast<const volatile int *>(a.err) != 0) { trace_end(a.trace); return; }
   const unsigned int e = a.epoch[a.net] + 1u;
   float *mine = a.tab->base[a.rank];
   unsigned int *my_flags = reinterpret_cast<unsigned int *>(mine + a.flag_off);

@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstring>
 #include <fstream>
+#include <mutex>
 #include <regex>
 
 #include "../../include/dqn_b200.h"
@@ -23,6 +24,12 @@
 namespace dqn {
 
 using namespace hfo;
+
+struct DQN::ShareGroup {
+  std::mutex mu;
+  std::vector<DQN *> members;
+  int n_actor = 0, n_critic = 0;
+};
 
 // dqn.cpp:21-31
 DEFINE_int32(seed, 0, "Seed the RNG. Default: time");
@@ -223,6 +230,11 @@ DQN::DQN(caffe::SolverParameter &actor_solver_param, caffe::SolverParameter &cri
 }
 
 DQN::~DQN() {
+  if (share_) {          // leave the sharing group: the others must not write through into a dead handle
+    std::lock_guard<std::mutex> lock(share_->mu);
+    auto &m = share_->members;
+    m.erase(std::remove(m.begin(), m.end(), this), m.end());
+  }
   drain_pending();
   dqnb_destroy(h_);
 }
@@ -371,6 +383,13 @@ std::pair<float, float> DQN::UpdateActorCritic() {
 
 void DQN::Update() {  // dqn.cpp:799-826
   if (memory_size() < FLAGS_memory_threshold) return;
+  if (share_) {          // multi-agent sharing: one member updates at a time, then its shared layers reach the others
+    std::lock_guard<std::mutex> lock(share_->mu);
+    last_update_ = UpdateActorCritic();
+    drain_pending();
+    for (DQN *m : share_->members)
+      if (m != this) DQNB_OK(dqnb_copy_shared_layers(m->h_, h_, share_->n_actor, share_->n_critic));
+  } else
   last_update_ = UpdateActorCritic();
   if (critic_iter() % FLAGS_loss_display_iter == 0) {
     LOG(INFO) << "[Agent" << tid_ << "] Critic Iteration " << critic_iter() << ", loss = " << smoothed_critic_loss_;
@@ -609,11 +628,51 @@ void DQN::LoadReplayMemory(const std::string &filename) {
 void DQN::ShareLayer(caffe::Layer<float> &, caffe::Layer<float> &) {
   LOG(FATAL) << "ShareLayer (dqn.cpp:1037-1046) takes Caffe layer objects, which do not exist in this build; use ShareParameters";
 }
-void DQN::ShareParameters(DQN &, int, int) {
-  LOG(FATAL) << "ShareParameters (dqn.cpp:1048-1079) is outside the hot-path scope of this build (SURVEY 8f-3)";
+// dqn.cpp:1048-1079.  Upstream the slave's blobs ShareData() with the owner's: one copy of the first n layers (and of the
+// same layers of the target nets) that every agent's solver updates in turn, each with its own Adam history.  Here every
+// DQN owns a handle with flat device buffers, so a group keeps the copies identical by writing through: `other` takes
+// the owner's layers now, and after each member's UpdateActorCritic its shared layers are copied to the other members
+// (DQN::Update, under the group's mutex: upstream's agent threads race on the shared blobs, this serialises them).
+void DQN::ShareParameters(DQN &other, int num_actor_layers_to_share, int num_critic_layers_to_share) {
+  CHECK(&other != this);
+  CHECK_GE(num_actor_layers_to_share, 0);
+  CHECK_GE(num_critic_layers_to_share, 0);
+  CHECK_LE(num_actor_layers_to_share, (int)hidden_.size() + 2) << "the actor has " << hidden_.size() + 2 << " layers with parameters";
+  CHECK_LE(num_critic_layers_to_share, (int)hidden_.size() + 1) << "the critic has " << hidden_.size() + 1 << " layers with parameters";
+  if (!share_) {
+    share_ = std::make_shared<ShareGroup>();
+    share_->members.push_back(this);
+    share_->n_actor = num_actor_layers_to_share;
+    share_->n_critic = num_critic_layers_to_share;
+  }
+  CHECK(share_->n_actor == num_actor_layers_to_share && share_->n_critic == num_critic_layers_to_share)
+      << "one sharing group shares one set of layers (dqn_main.cpp:311 passes the same flags for every teammate)";
+  std::lock_guard<std::mutex> lock(share_->mu);
+  static const char *kActorNames[] = {"action_layer", "actionpara_layer"};
+  for (int i = 0; i < num_actor_layers_to_share; ++i)
+    LOG(INFO) << "Sharing Actor Layer " << (i < (int)hidden_.size() ? "ip" + std::to_string(i + 1) + "_layer" : std::string(kActorNames[i - hidden_.size()]));
+  for (int i = 0; i < num_critic_layers_to_share; ++i)
+    LOG(INFO) << "Sharing Critic Layer " << (i < (int)hidden_.size() ? "ip" + std::to_string(i + 1) + "_layer" : std::string("q_values_layer"));
+  drain_pending();
+  other.drain_pending();
+  DQNB_OK(dqnb_copy_shared_layers(other.h_, h_, num_actor_layers_to_share, num_critic_layers_to_share));
+  other.share_ = share_;
+  share_->members.push_back(&other);
 }
-void DQN::ShareReplayMemory(DQN &) {
-  LOG(FATAL) << "ShareReplayMemory (dqn.cpp:1081-1083) is outside the hot-path scope of this build (SURVEY 8f-3)";
+// dqn.cpp:1081-1083: `other.replay_memory_ = replay_memory_` is a COPY of the deque (of shared_ptr states) at the time of
+// the call, not an alias: the two memories diverge afterwards.
+void DQN::ShareReplayMemory(DQN &other) {
+  CHECK(&other != this);
+  CHECK_EQ(state_size_, other.state_size_);
+  other.ClearReplayMemory();
+  const int n = memory_size(), S = state_size_, chunk = 16384;
+  std::vector<float> s((size_t)chunk * S), sn((size_t)chunk * S), a((size_t)chunk * (kActionSize + kActionParamSize)), r(chunk), mc(chunk);
+  std::vector<uint8_t> term(chunk);
+  for (int first = 0; first < n; first += chunk) {
+    const int m = std::min(chunk, n - first);
+    DQNB_OK(dqnb_get_transitions(h_, first, m, s.data(), a.data(), r.data(), mc.data(), sn.data(), term.data()));
+    DQNB_OK(dqnb_add_transitions(other.h_, m, s.data(), a.data(), r.data(), mc.data(), sn.data(), term.data()));
+  }
 }
 
 }  // namespace dqn

@@ -137,6 +137,10 @@ class DQN {
   void load_weights(int net, const std::string &file);
   void restore_solver(int net, const std::string &file);
   void drain_pending();
+  // Multi-agent sharing: every member of a group sees the first n layers of the group's nets as one set of weights
+  // (ShareData aliases memory upstream; here the member that just updated writes its shared layers through to the others)
+  struct ShareGroup;
+  std::shared_ptr<ShareGroup> share_;
   long long pending_step_ = 0;   // -async_update: sequence number of the update whose results are still to be read
 };
 

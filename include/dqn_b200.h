@@ -87,6 +87,12 @@ int dqnb_get_params(dqnb_handle h, int net, float *params);
 int dqnb_init_params(dqnb_handle h, uint64_t seed, float std);
 /* CloneNet(critic->critic_target), CloneNet(actor->actor_target) (dqn.cpp:660-661). */
 int dqnb_clone_targets(dqnb_handle h);
+/* ShareParameters (dqn.cpp:1048-1079; ShareLayer :1037-1046 -> Blob::ShareData): the first n layers-with-parameters
+ * (Caffe layer order: ip1..ipK, then action_layer, actionpara_layer | q_values_layer) of src's actor / critic AND of
+ * their target nets overwrite dst's.  Blob::ShareData aliases memory; two handles cannot alias sub-ranges of a flat
+ * buffer, so a sharing group calls this after each member's update (write-through; host/dqn.cpp ShareParameters).
+ * Both handles are synchronised; dst's act-path snapshot of the actor is refreshed. */
+int dqnb_copy_shared_layers(dqnb_handle dst, dqnb_handle src, int32_t n_actor_layers, int32_t n_critic_layers);
 /* Solver::Restore / Snapshot state: Adam history (m, v) and iter (dqn.cpp:545,:554,:589-590). */
 int dqnb_set_opt_state(dqnb_handle h, int net, const float *m, const float *v, int32_t iter);
 int dqnb_get_opt_state(dqnb_handle h, int net, float *m, float *v, int32_t *iter);

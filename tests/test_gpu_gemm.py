@@ -70,3 +70,23 @@ def test_gemm_exact_on_small_integers():
         Bin = np.ascontiguousarray(B.T) if b_mn else B
         Cm, _ = P.gemm_test(0, a_mn, b_mn, M, N, K, 1, Ain, Bin)
         assert np.array_equal(Cm, ref), (a_mn, b_mn, np.abs(Cm - ref).max())
+
+
+@pytest.mark.parametrize("bn", [32, 64, 128])
+@pytest.mark.parametrize("b_mn,M,N,K,splits", [(0, 1024, 512, 1024, 1), (1, 1024, 1024, 512, 1), (0, 256, 192, 96, 1), (0, 128, 64, 4096, 8),
+                                               (1, 128, 128, 32, 1), (0, 1024, 256, 544, 2)])
+def test_gemm_a_in_tensor_memory(bn, b_mn, M, N, K, splits):
+    """A-in-TMEM mainloop (K-major A copied shared -> tensor memory by the mover warps, tcgen05.mma reads it there):
+    same products as the shared-memory mode, for K-major and MN-major B, ragged K splits and a single k-block."""
+    P = pkg()
+    rng = np.random.default_rng(11 * M + N + K + bn + b_mn)
+    A = rng.normal(0, 1, (M, K)).astype(np.float32)
+    B = rng.normal(0, 1, (N, K)).astype(np.float32)
+    ref = A.astype(np.float64) @ B.astype(np.float64).T
+    Bin = np.ascontiguousarray(B.T) if b_mn else B
+    Cm, ms = P.gemm_test(0 | (4 << 8) | (bn << 16), 0, b_mn, M, N, K, splits, A, Bin)
+    assert relerr(Cm, ref) < 2e-5, (relerr(Cm, ref), ms)
+    Ai = rng.integers(-4, 5, (M, K)).astype(np.float32)
+    Bi = rng.integers(-4, 5, (N, K)).astype(np.float32)
+    Ci, _ = P.gemm_test(0 | (4 << 8) | (bn << 16), 0, b_mn, M, N, K, splits, Ai, np.ascontiguousarray(Bi.T) if b_mn else Bi)
+    assert np.array_equal(Ci, (Ai.astype(np.int64) @ Bi.astype(np.int64).T).astype(np.float32))
