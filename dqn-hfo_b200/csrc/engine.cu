@@ -272,6 +272,8 @@ struct dqnb_handle_s {
   long long x_in[2] = {0, 0}, x_out[2] = {0, 0}, x_flag = 0;
   P2PTable *p2p_tab = nullptr; unsigned int *p2p_epoch = nullptr, *p2p_ticket = nullptr;
   int *p2p_err = nullptr; volatile int *h_p2p_err = nullptr;   // sticky exchange-failure flag: host-mapped pinned word
+  int *p2p_err_dev = nullptr;                                  // ... and its device-resident twin, the one kernels READ
+                                                               // (a read of mapped host memory costs ~1 us and they serialise)
   float *p2p_block_ss = nullptr;
   std::vector<void *> ipc_opened;
   int comm_mode = 0;                  // 0 none, 1 NCCL all-reduce, 2 P2P exchange kernel
@@ -793,7 +795,7 @@ static void build_solver(dqnb_handle_s *h, int is_critic, const SegTable &segs, 
       memset(&x, 0, sizeof(x));
       x.tab = h->p2p_tab; x.world = h->cfg.world_size; x.rank = h->cfg.rank; x.net = is_critic;
       x.in_off = h->x_in[is_critic]; x.out_off = h->x_out[is_critic]; x.flag_off = h->x_flag;
-      x.count = g.flat + 4; x.epoch = h->p2p_epoch; x.ticket = h->p2p_ticket; x.err = h->p2p_err;
+      x.count = g.flat + 4; x.epoch = h->p2p_epoch; x.ticket = h->p2p_ticket; x.err = h->p2p_err; x.err_dev = h->p2p_err_dev;
       x.timeout_ns = (unsigned long long)std::max(1, env_int("DQNB_P2P_TIMEOUT_MS", 20000)) * 1000000ull;
       x.block_ss = h->p2p_block_ss;
       ar.blocks = 128;
@@ -818,7 +820,7 @@ static void build_solver(dqnb_handle_s *h, int is_critic, const SegTable &segs, 
   d.P = h->P[is_critic ? DQNB_CRITIC : DQNB_ACTOR]; d.p_plane = g.flat;
   d.T = h->P[is_critic ? DQNB_CRITIC_TARGET : DQNB_ACTOR_TARGET]; d.t_plane = g.flat;
   d.st = h->st; d.st_out = h->st; d.is_critic = is_critic; d.hp = h->hp;
-  d.comm_err = (multi && h->comm_mode == 2) ? h->p2p_err : nullptr;
+  d.comm_err = (multi && h->comm_mode == 2) ? h->p2p_err_dev : nullptr;
   ad.blocks = blocks;
   ops.push_back(ad);
 }
@@ -1190,7 +1192,7 @@ static int create_impl(const dqnb_config *cfg, dqnb_handle_s *h) {
     if (dalloc(h, &h->xchg, (size_t)h->xchg_floats)) return -1;
     for (int n = 0; n < 2; ++n) { h->G[n] = h->xchg + h->x_in[n]; h->Gr[n] = h->G[n]; }
     if (dalloc(h, &h->p2p_tab, 1) || dalloc(h, &h->p2p_epoch, 2) || dalloc(h, &h->p2p_ticket, 2) ||
-        dalloc(h, &h->p2p_block_ss, 2 * 256)) return -1;
+        dalloc(h, &h->p2p_block_ss, 2 * 256) || dalloc(h, &h->p2p_err_dev, 1)) return -1;
     {
       void *hp = nullptr, *dp = nullptr;
       DQNB_CUDA(cudaHostAlloc(&hp, 64, cudaHostAllocMapped));

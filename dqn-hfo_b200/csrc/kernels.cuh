@@ -716,7 +716,8 @@ struct P2PArgs {
   long long count;                // floats to reduce (multiple of 4)
   unsigned int *epoch;            // [2] per net, local memory
   unsigned int *ticket;           // [2] per net, local memory
-  int *err;                       // host-mapped, sticky
+  int *err;                       // host-mapped, sticky: written on a timeout, read by the host only
+  int *err_dev;                   // device-resident twin: what kernels read
   unsigned long long timeout_ns;
 };
 __device__ __forceinline__ unsigned int ld_acquire_sys_u32(const unsigned int *p) {
@@ -732,7 +733,7 @@ __device__ __forceinline__ float4 ld_volatile_f4(const float *p) {
   asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ bool spin_until_ge(const unsigned int *flag, unsigned int target, int *err, unsigned long long timeout_ns) {
+__device__ __forceinline__ bool spin_until_ge(const unsigned int *flag, unsigned int target, int *err, int *err_dev, unsigned long long timeout_ns) {
   unsigned long long t0;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
   while (ld_acquire_sys_u32(flag) < target) {
@@ -740,7 +741,12 @@ __device__ __forceinline__ bool spin_until_ge(const unsigned int *flag, unsigned
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
     // a peer is gone (or later than DQNB_P2P_TIMEOUT_MS): give up instead of hanging the GPU.  The flag is sticky and
     // host-visible: the optimiser kernels skip their update once it is set and dqnb_update / dqnb_results fail.
-    if (t1 - t0 > timeout_ns) { *reinterpret_cast<volatile int *>(err) = 1; __threadfence_system(); return false; }
+    if (t1 - t0 > timeout_ns) {
+      *reinterpret_cast<volatile int *>(err_dev) = 1;
+      *reinterpret_cast<volatile int *>(err) = 1;
+      __threadfence_system();
+      return false;
+    }
     __nanosleep(64);
   }
   return true;
@@ -752,7 +758,7 @@ __global__ void __launch_bounds__(512) p2p_allreduce_kernel(const P2PArgs a) {
   const int W = a.world;
   // a peer already missed its timeout (sticky, set before this launch): the replicas have stopped updating
   // (adam_kernel skips), so later exchanges return at once instead of waiting out the timeout again
-  if (*reinterpret_cast<const volatile int *>(a.err) != 0) { trace_end(a.trace); return; }
+  if (*reinterpret_cast<const volatile int *>(a.err_dev) != 0) { trace_end(a.trace); return; }
   const unsigned int e = a.epoch[a.net] + 1u;
   float *mine = a.tab->base[a.rank];
   unsigned int *my_flags = reinterpret_cast<unsigned int *>(mine + a.flag_off);
@@ -763,7 +769,7 @@ __global__ void __launch_bounds__(512) p2p_allreduce_kernel(const P2PArgs a) {
     unsigned int *pf = reinterpret_cast<unsigned int *>(a.tab->base[threadIdx.x] + a.flag_off) + a.net * kMaxPeers;
     st_release_sys_u32(pf + a.rank, e);
   }
-  if (threadIdx.x < W) spin_until_ge(my_flagA + threadIdx.x, e, a.err, a.timeout_ns);
+  if (threadIdx.x < W) spin_until_ge(my_flagA + threadIdx.x, e, a.err, a.err_dev, a.timeout_ns);
   __syncthreads();
   // B
   const long long n4 = a.count / 4, per = (n4 + W - 1) / W;
@@ -827,7 +833,7 @@ __global__ void __launch_bounds__(512) p2p_allreduce_kernel(const P2PArgs a) {
     __threadfence_system();
     unsigned int *pf = reinterpret_cast<unsigned int *>(a.tab->base[threadIdx.x] + a.flag_off) + 2 * kMaxPeers + a.net * kMaxPeers;
     st_release_sys_u32(pf + a.rank, e);
-    spin_until_ge(my_flagB + threadIdx.x, e, a.err, a.timeout_ns);
+    spin_until_ge(my_flagB + threadIdx.x, e, a.err, a.err_dev, a.timeout_ns);
   }
   __syncthreads();
   if (threadIdx.x == 0) { a.ticket[a.net] = 0; a.epoch[a.net] = e; __threadfence(); }

@@ -45,3 +45,36 @@ def test_parity_checker_single_rank():
     assert res["ok"], res
     res = dp_parity.check(pkg(), None, torch, 0, 1, 0, 58, 256, (256, 128, 64, 64), n_updates=2, frozen=False)
     assert res["ok"], res
+
+
+def _cfg4(n, port):
+    script = os.path.join(ROOT, "scripts", "cfg4_rollout.py")
+    if n == 1:
+        cmd = [sys.executable, script]
+    else:
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n),
+               "--master-addr", "127.0.0.1", "--master-port", str(port), script]
+    return subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+
+
+def test_cfg4_rollout_single_gpu():
+    """BASELINE cfg4 on one GPU: 64 workers, act path beside asynchronous updates, replay appends on the copy stream."""
+    out = _cfg4(1, 0)
+    assert "CFG4_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
+
+
+def test_cfg4_rollout_two_ranks():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    out = _cfg4(2, 29541)
+    assert "CFG4_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
+
+
+def test_cfg4_rollout_eight_ranks():
+    """BASELINE cfg4 as specified: 64 workers -> 8-GPU sharded replay, 8 workers per rank."""
+    import torch
+    if torch.cuda.device_count() < 8:
+        pytest.skip("needs 8 GPUs (gpurun --gpus 8)")
+    out = _cfg4(8, 29542)
+    assert "CFG4_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
