@@ -270,6 +270,7 @@ struct dqnb_handle_s {
   float *Gr[2] = {nullptr, nullptr};  // gradient the optimiser consumes: G, or the all-reduced copy (P2P exchange)
   float *xchg = nullptr; long long xchg_floats = 0;   // IPC-exportable exchange allocation (world_size > 1)
   long long x_in[2] = {0, 0}, x_out[2] = {0, 0}, x_flag = 0;
+  unsigned int *flag_ticket = nullptr;
   P2PTable *p2p_tab = nullptr; unsigned int *p2p_epoch = nullptr, *p2p_ticket = nullptr;
   int *p2p_err = nullptr; volatile int *h_p2p_err = nullptr;   // sticky exchange-failure flag: host-mapped pinned word
   int *p2p_err_dev = nullptr;                                  // ... and its device-resident twin, the one kernels READ
@@ -795,6 +796,9 @@ static void build_solver(dqnb_handle_s *h, int is_critic, const SegTable &segs, 
       memset(&x, 0, sizeof(x));
       x.tab = h->p2p_tab; x.world = h->cfg.world_size; x.rank = h->cfg.rank; x.net = is_critic;
       x.in_off = h->x_in[is_critic]; x.out_off = h->x_out[is_critic]; x.flag_off = h->x_flag;
+      ReduceArgs &ra = ops.back().red;      // the reduction in front of the exchange releases flag A
+      ra.tab = h->p2p_tab; ra.world = h->cfg.world_size; ra.rank = h->cfg.rank; ra.net = is_critic; ra.flag_off = h->x_flag;
+      ra.epoch = h->p2p_epoch; ra.flag_ticket = h->flag_ticket;
       x.count = g.flat + 4; x.epoch = h->p2p_epoch; x.ticket = h->p2p_ticket; x.err = h->p2p_err; x.err_dev = h->p2p_err_dev;
       x.timeout_ns = (unsigned long long)std::max(1, env_int("DQNB_P2P_TIMEOUT_MS", 20000)) * 1000000ull;
       x.block_ss = h->p2p_block_ss;
@@ -1192,7 +1196,7 @@ static int create_impl(const dqnb_config *cfg, dqnb_handle_s *h) {
     if (dalloc(h, &h->xchg, (size_t)h->xchg_floats)) return -1;
     for (int n = 0; n < 2; ++n) { h->G[n] = h->xchg + h->x_in[n]; h->Gr[n] = h->G[n]; }
     if (dalloc(h, &h->p2p_tab, 1) || dalloc(h, &h->p2p_epoch, 2) || dalloc(h, &h->p2p_ticket, 2) ||
-        dalloc(h, &h->p2p_block_ss, 2 * 256) || dalloc(h, &h->p2p_err_dev, 1)) return -1;
+        dalloc(h, &h->p2p_block_ss, 2 * 256) || dalloc(h, &h->p2p_err_dev, 1) || dalloc(h, &h->flag_ticket, 2)) return -1;
     {
       void *hp = nullptr, *dp = nullptr;
       DQNB_CUDA(cudaHostAlloc(&hp, 64, cudaHostAllocMapped));

@@ -477,6 +477,26 @@ __global__ void __launch_bounds__(1024) colsum_kernel(const ColsumArgs a) {
   trace_end(a.trace);
 }
 
+// peer table + system-scope flag helpers of the multi-GPU gradient exchange (p2p_allreduce_kernel below); the gradient
+// reduction in front of it already tells the peers that this rank's gradient is complete
+constexpr int kMaxPeers = 8;
+struct P2PTable {                 // device-resident, filled by dqnb_comm_p2p_init
+  float *base[kMaxPeers];         // peer exchange allocations (IPC-mapped); base[rank] is our own
+};
+__device__ __forceinline__ unsigned int ld_acquire_sys_u32(const unsigned int *p) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys_u32(unsigned int *p, unsigned int v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ float4 ld_volatile_f4(const float *p) {
+  float4 v;
+  asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+
 // -------------------------------------------------------------------------------------------
 // Gradient reduction over split planes + sum of squares (SGDSolver::ClipGradients numerator).
 struct SegTable {
@@ -498,6 +518,10 @@ struct ReduceArgs {
   int do_reduce, do_sumsq;
   // the critic's reduction (first optimiser kernel of an update) also refreshes the per-update Adam scalars
   int do_prep; StepState *st; HyperParams hp;
+  // data-parallel runs with the peer-memory exchange: the last block releases flag A ("my gradient is complete") to
+  // every peer, one kernel boundary earlier than the exchange kernel could
+  const P2PTable *tab; int world, rank, net; long long flag_off;
+  const unsigned int *epoch; unsigned int *flag_ticket;
 };
 __global__ void __launch_bounds__(256) reduce_kernel(const ReduceArgs a) {
   DQNB_PDL_PROLOGUE();
@@ -558,6 +582,22 @@ __global__ void __launch_bounds__(256) reduce_kernel(const ReduceArgs a) {
     st->step_actor = __fmul_rn(a.hp.actor_lr, ca);
     const int mx = max(ta, tc);       // max_iter() after both solvers stepped (dqn.cpp:967)
     st->do_soft = (a.hp.soft_update_freq > 0 && mx % a.hp.soft_update_freq == 0) ? 1 : 0;
+  }
+  if (a.tab) {
+    __shared__ int s_last_blk;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last_blk = (atomicAdd(a.flag_ticket + a.net, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (s_last_blk) {
+      __threadfence();
+      if ((int)threadIdx.x < a.world) {
+        const unsigned int e = a.epoch[a.net] + 1u;
+        unsigned int *pf = reinterpret_cast<unsigned int *>(a.tab->base[threadIdx.x] + a.flag_off) + a.net * kMaxPeers;
+        st_release_sys_u32(pf + a.rank, e);
+      }
+      if (threadIdx.x == 0) a.flag_ticket[a.net] = 0;
+    }
   }
   trace_end(a.trace);
 }
@@ -702,10 +742,6 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamArgs a) {
 //      when the kernel retires, the whole reduced gradient is in this rank's output buffer.
 // Epochs are device-resident and advance once per call, so the kernel is CUDA-graph replayable.  Every
 // spin has a timeout (err flag) so that a missing peer cannot wedge the GPU.
-constexpr int kMaxPeers = 8;
-struct P2PTable {                 // device-resident, filled by dqnb_comm_p2p_init
-  float *base[kMaxPeers];         // peer exchange allocations (IPC-mapped); base[rank] is our own
-};
 struct P2PArgs {
   long long *trace;              // DQNB_TRACE timeline slot (nullable)
   const P2PTable *tab;
@@ -720,19 +756,6 @@ struct P2PArgs {
   int *err_dev;                   // device-resident twin: what kernels read
   unsigned long long timeout_ns;
 };
-__device__ __forceinline__ unsigned int ld_acquire_sys_u32(const unsigned int *p) {
-  unsigned int v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_sys_u32(unsigned int *p, unsigned int v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ float4 ld_volatile_f4(const float *p) {
-  float4 v;
-  asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
-  return v;
-}
 __device__ __forceinline__ bool spin_until_ge(const unsigned int *flag, unsigned int target, int *err, int *err_dev, unsigned long long timeout_ns) {
   unsigned long long t0;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
@@ -763,14 +786,10 @@ __global__ void __launch_bounds__(512) p2p_allreduce_kernel(const P2PArgs a) {
   float *mine = a.tab->base[a.rank];
   unsigned int *my_flags = reinterpret_cast<unsigned int *>(mine + a.flag_off);
   unsigned int *my_flagA = my_flags + a.net * kMaxPeers, *my_flagB = my_flags + 2 * kMaxPeers + a.net * kMaxPeers;
-  // A
-  if (blockIdx.x == 0 && threadIdx.x < W) {
-    __threadfence_system();
-    unsigned int *pf = reinterpret_cast<unsigned int *>(a.tab->base[threadIdx.x] + a.flag_off) + a.net * kMaxPeers;
-    st_release_sys_u32(pf + a.rank, e);
-  }
+  // A: flag A was released by the last block of the gradient reduction in front of this kernel
   if (threadIdx.x < W) spin_until_ge(my_flagA + threadIdx.x, e, a.err, a.err_dev, a.timeout_ns);
   __syncthreads();
+  if (a.trace && blockIdx.x == 0 && threadIdx.x == 0) a.trace[3] = (long long)gtime_ns();
   // B
   const long long n4 = a.count / 4, per = (n4 + W - 1) / W;
   const long long lo = (long long)a.rank * per, hi = min(n4, lo + per);
@@ -815,8 +834,10 @@ __global__ void __launch_bounds__(512) p2p_allreduce_kernel(const P2PArgs a) {
     }
   }
   // C
-  __threadfence_system();
+  if (a.trace && blockIdx.x == 0 && threadIdx.x == 0) a.trace[4] = (long long)gtime_ns();
+  __threadfence_system();            // this block's remote stores are acknowledged (one NVLink round trip behind the data)
   __syncthreads();
+  if (a.trace && blockIdx.x == 0 && threadIdx.x == 0) a.trace[5] = (long long)gtime_ns();
   if (threadIdx.x == 0) {
     const unsigned int t = atomicAdd(a.ticket + a.net, 1u);
     s_last = (t == gridDim.x - 1);
@@ -824,18 +845,32 @@ __global__ void __launch_bounds__(512) p2p_allreduce_kernel(const P2PArgs a) {
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  if (threadIdx.x < W) {
-    // this rank's share of ||g||^2, summed over its blocks in fixed order, travels with the completion flag
+  if (a.trace && threadIdx.x == 0) a.trace[8] = (long long)gtime_ns();
+  {
+    // this rank's share of ||g||^2 travels with the completion flag.  The per-block partials are summed by a fixed
+    // tree (thread b holds block b, b + 512, ..; warp shuffles; warps in order): the same bits on every run.  (A serial
+    // loop of volatile loads in the signalling threads cost 6.6 us here.)
+    __shared__ float red2[16];
     float s = 0.f;
-    for (int b = 0; b < (int)gridDim.x; ++b) s += reinterpret_cast<volatile float *>(a.block_ss)[a.net * gridDim.x + b];
-    float *pn = a.tab->base[threadIdx.x] + a.flag_off + 4 * kMaxPeers + a.net * kMaxPeers;
-    reinterpret_cast<volatile float *>(pn)[a.rank] = s;
-    __threadfence_system();
-    unsigned int *pf = reinterpret_cast<unsigned int *>(a.tab->base[threadIdx.x] + a.flag_off) + 2 * kMaxPeers + a.net * kMaxPeers;
-    st_release_sys_u32(pf + a.rank, e);
-    spin_until_ge(my_flagB + threadIdx.x, e, a.err, a.err_dev, a.timeout_ns);
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) s += reinterpret_cast<volatile float *>(a.block_ss)[a.net * gridDim.x + b];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red2[threadIdx.x >> 5] = s;
+    __syncthreads();
+    s = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red2[w];
+    if (threadIdx.x < W) {
+      float *pn = a.tab->base[threadIdx.x] + a.flag_off + 4 * kMaxPeers + a.net * kMaxPeers;
+      reinterpret_cast<volatile float *>(pn)[a.rank] = s;
+      // st.release orders this thread's norm store (and, through the ticket and the fences above, every block's slice
+      // stores) before the flag: no second system fence
+      unsigned int *pf = reinterpret_cast<unsigned int *>(a.tab->base[threadIdx.x] + a.flag_off) + 2 * kMaxPeers + a.net * kMaxPeers;
+      st_release_sys_u32(pf + a.rank, e);
+      if (a.trace && threadIdx.x == 0) a.trace[9] = (long long)gtime_ns();
+      spin_until_ge(my_flagB + threadIdx.x, e, a.err, a.err_dev, a.timeout_ns);
+    }
   }
   __syncthreads();
+  if (a.trace && threadIdx.x == 0) a.trace[10] = (long long)gtime_ns();
   if (threadIdx.x == 0) { a.ticket[a.net] = 0; a.epoch[a.net] = e; __threadfence(); }
 }
 

@@ -21,7 +21,19 @@ if len(sys.argv) > 2:          # knob overrides, e.g. '{"DQNB_SCHED": 1}'
     for k, v in json.loads(sys.argv[2]).items():
         os.environ[k] = str(v)
     print("knobs:", sys.argv[2])
-d = P.DQNB(state_size=58, batch=B, hidden=(1024, 512, 256, 128), replay_capacity=70000, use_graph=1)
+rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+if world > 1:          # under torchrun: the data-parallel step (exchange kernels in the timeline); rank 0 prints
+    import torch
+    import torch.distributed as dist
+    from scripts import dp_parity
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if rank != 0:
+        sys.stdout = open(os.devnull, "w")
+d = P.DQNB(device=local, state_size=58, batch=B, hidden=(1024, 512, 256, 128), replay_capacity=70000, use_graph=1, world_size=world, rank=rank,
+           seed=3 + rank)
+if world > 1:
+    dp_parity.connect(P, d, "p2p", rank, world, dist, torch)
 d.init_params(2, 0.01)
 s, a, r, mc, term, sn = synth_replay(65536, 58, 1)
 d.add_transitions(s, a, r, mc, sn, term)
@@ -54,6 +66,10 @@ for i in range(len(t)):
               f"{us(t[i,3]):6.1f}({us(t[i,8]):6.1f}) {us(t[i,4]):6.1f}({us(t[i,9]):6.1f}) {us(t[i,5]):6.1f}({us(t[i,10]):6.1f}) {us(t[i,6]):8.1f} | {us(t[i,6]) - us(t[i,2]):6.1f}"
               f" | epi: acc+{us(t[i,11]) - us(t[i,4]):4.2f} staged+{us(t[i,12]) - us(t[i,11]):4.2f} stored+{us(t[i,5]) - us(t[i,12]):4.2f} synced+{us(t[i,13]) - us(t[i,5]):4.2f}")
     else:
+        extra = ""
+        if name == "P2P_ALLREDUCE":
+            extra = (f" | flagA +{us(t[i,3]) - us(t[i,0]):4.1f}  summed +{us(t[i,4]) - us(t[i,3]):4.1f}  fenced +{us(t[i,5]) - us(t[i,4]):4.1f}"
+                     f"  last block +{us(t[i,8]) - us(t[i,5]):4.1f}  flagB sent +{us(t[i,9]) - us(t[i,8]):4.1f}  flagB seen +{us(t[i,10]) - us(t[i,9]):4.1f}")
         print(f"{i:3d} {name:16s} {br}                  | {'':7s} {us(t[i,0]):6.1f}({us(t[i,1]):6.1f}) {'':14s} {'':14s} {'':14s} {us(t[i,2]):8.1f} | "
-              f"{us(t[i,2]) - us(t[i,0]):6.1f}")
+              f"{us(t[i,2]) - us(t[i,0]):6.1f}{extra}")
 d.close()
