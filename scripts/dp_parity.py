@@ -111,10 +111,15 @@ def check(P, dist, torch, rank, world, local, S, B, hidden, comm="p2p", n_update
             for k in ("a_pi",):
                 note(k, relerr(taps[k], t[k]), RTOL if strict else 30 * RTOL)
             if frozen:
+                # ReLU-kink rows (tests/util.py relerr_robust, tests/test_oracle_autograd.py): a row whose critic has a
+                # pre-activation within rounding (~1e-6 relative for 3xTF32) of zero takes slope 1 here and 0.01 there,
+                # which moves that row's action gradient by percents.  Expected share of such rows ~ hidden units per
+                # row x 1e-6: 0.15 % at 1024-512-256-128, 0.35 % at 1024x4 -> the bound is on the 99th percentile.
                 for k in ("q_pi", "d_raw", "d_inv"):
                     e = np.sort(np.abs(np.asarray(taps[k], np.float64).ravel() - np.asarray(t[k], np.float64).ravel())) \
                         / (np.abs(t[k]).max() + 1e-30)
-                    note(k + "_p998", e[int(np.ceil(e.size * 0.998)) - 1], RTOL)   # ReLU-kink rows, see tests/util.py
+                    note(k + "_p99", e[int(np.ceil(e.size * 0.99)) - 1], RTOL)
+                    note(k + "_median", e[e.size // 2], 0.1 * RTOL)
                     note(k + "_max", e[-1], 0.3)
                 for k in ("critic_grad", "actor_grad"):
                     got = d.debug_read(k, t[k].size)

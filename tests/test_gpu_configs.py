@@ -38,9 +38,12 @@ def test_frozen_weights_every_intermediate_matches(name):
     assert abs(avgq - oavgq) <= RTOL * abs(oavgq) + 1e-6, (avgq, oavgq)
     for key, n in (("y", B), ("q", B), ("a_pi", B * 10), ("q_pi", B), ("critic_grad", t["critic_grad"].size)):
         assert relerr(d.debug_read(key, n), t[key]) < RTOL, key
+    # action gradients: rows with a ReLU-kink flip differ by percents (expected share of rows ~ hidden units per row x
+    # 1e-6, i.e. 0.15-0.35 % here; tests/test_oracle_autograd.py shows the fp32 oracle doing the same against float64)
     for key, n in (("d_raw", B * 10), ("d_inv", B * 10), ("actor_grad", t["actor_grad"].size)):
         got = d.debug_read(key, n)
-        assert relerr_robust(got, t[key]) < RTOL, (key, relerr_robust(got, t[key]))
+        assert relerr_robust(got, t[key], frac=1e-2) < RTOL, (key, relerr_robust(got, t[key], frac=1e-2))
+        assert relerr_robust(got, t[key], frac=0.5) < 0.1 * RTOL, (key, relerr_robust(got, t[key], frac=0.5))   # median
         assert relerr(got, t[key]) < 0.3, (key, relerr(got, t[key]))
     assert compare_state(st, d)["iters"] == (1, 1)
     d.close()
