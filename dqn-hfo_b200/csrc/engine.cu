@@ -401,6 +401,7 @@ struct Tuning {
   int ts_min_kb;        // forward / dX GEMMs with at least this many k-blocks per CTA run in A-in-TMEM mode (0 < x; 9999 = never)
   int bn32_max_tiles;   // forward / dX GEMMs with at most this many 128x64 output tiles use 128x32 tiles instead
   int bn32_cluster;     // 1: such GEMMs may still split K over a 2-CTA cluster
+  int dw_big_max_ctas;  // CTA budget of the split-K choice for the big weight-gradient GEMMs (>= 32 output tiles)
   int dw_after_dx;  // bit l: the weight-gradient GEMM of tower layer l waits for the end of the dX chain (dZ[0])
   int bn_side_l1;   // N tile of a side chain's first layer: 128 halves its CTA count (128 -> 64), so that it fits beside
                     // the critical chain's second layer (64 CTAs) instead of queueing in front of it
@@ -421,6 +422,7 @@ struct Tuning {
     ts_min_kb = env_int("DQNB_TS_MIN_KB", 8);
     bn32_max_tiles = env_int("DQNB_BN32_MAX_TILES", 32);
     bn32_cluster = env_int("DQNB_BN32_CLUSTER", 0);
+    dw_big_max_ctas = env_int("DQNB_DW_BIG_MAX_CTAS", 160);
     dw_after_dx = env_int("DQNB_DW_AFTER_DX", 0);
     bn_side_l1 = env_int("DQNB_BN_SIDE_L1", 128);
     bn_dx = env_int("DQNB_BN_DX", 64);
@@ -440,9 +442,9 @@ static const Tuning &tuning() {
 // ---------------------------------------------------------------------------------------------
 // GEMM op builders
 // ---------------------------------------------------------------------------------------------
-static int pick_splits(int tiles, int kblocks, int max_splits) {
+static int pick_splits(int tiles, int kblocks, int max_splits, int max_ctas = 160) {
   int s = 1;
-  while (s * 2 <= max_splits && tiles * s * 2 <= 160 && kblocks / (s * 2) >= 2) s *= 2;
+  while (s * 2 <= max_splits && tiles * s * 2 <= max_ctas && kblocks / (s * 2) >= 2) s *= 2;
   return s;
 }
 
@@ -467,7 +469,9 @@ static int finish_gemm(const dqnb_config &cfg, Op *op) {
     // (DSMEM reduction in the epilogue) so that the dependent chain sees half the mainloop latency.
     {
       const int tiles = ((p.M + BM - 1) / BM) * ((p.N + p.bn - 1) / p.bn);
-      if (p.epi != EPI_PLAIN && p.splits == 1 && p.K / BK >= 16 && 2 * tiles <= 148 && cfg.use_graph >= 0 &&
+      const bool no_cluster = p.cluster_k < 0;
+      p.cluster_k = 0;
+      if (!no_cluster && p.epi != EPI_PLAIN && p.splits == 1 && p.K / BK >= 16 && 2 * tiles <= 148 && cfg.use_graph >= 0 &&
           (!narrow || tuning().bn32_cluster) &&
           !getenv("DQNB_NO_CLUSTER_SPLITK")) {
         p.cluster_k = 1;
@@ -514,7 +518,7 @@ static int op_dx(const dqnb_config &cfg, const NetGeom &g, int l, const float *P
   memset(&p, 0, sizeof(p));
   p.bn = (tuning().bn_dx == 128 && L.Kp % 128 == 0) ? 128 : 64;
   p.stages = tuning().st_dx;
-  if (tuning().bn_big == 128 && L.Kp % 128 == 0 && ((dZl.rows + BM - 1) / BM) * (L.Kp / 64) >= 128) { p.bn = 128; p.stages = 0; }
+  if (tuning().bn_big == 128 && L.Kp % 128 == 0 && ((dZl.rows + BM - 1) / BM) * (L.Kp / 64) >= 128) { p.bn = 128; p.stages = 0; p.cluster_k = -1; }
   p.M = dZl.rows; p.N = L.Kp; p.K = L.Np; p.a_mn = 0; p.b_mn = 1; p.splits = 1; p.epi = EPI_DX;
   p.A = dZl.p; p.a_plane = dZl.plane(); p.lda = dZl.ld;
   p.B = P + L.w_off; p.b_plane = g.flat; p.ldb = L.Kp;
@@ -550,7 +554,7 @@ static int op_dw(const dqnb_config &cfg, const NetGeom &g, int l, const SplitMat
   p.stages = tuning().st_dw;
   if (tuning().bn_big == 128 && L.Kp % 128 == 0 && ((L.Np + BM - 1) / BM) * (L.Kp / 64) >= 64) { p.bn = 128; p.stages = 0; }
   const int tiles = ((p.M + BM - 1) / BM) * ((p.N + p.bn - 1) / p.bn);
-  p.splits = pick_splits(tiles, p.K / BK, kGradSplits);
+  p.splits = pick_splits(tiles, p.K / BK, kGradSplits, tiles >= 32 ? tuning().dw_big_max_ctas : 160);
   *splits_out = p.splits;
   p.A = dZl.p; p.a_plane = dZl.plane(); p.lda = dZl.ld;
   p.B = Xin.p; p.b_plane = Xin.plane(); p.ldb = Xin.ld;
