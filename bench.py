@@ -349,6 +349,15 @@ def main():
     barrier()
     ms_max = float(np.median(windows))
     value = B * world * args.steps / (ms_max * 1e-3)
+    # roofline leg, taken right here under the same clocks as the timed windows (after the cuBLAS peak measurement
+    # further down the GPU sits at its power cap for a while: the same replay then reads 13 instead of 8.7 us per launch)
+    gemm_ms = n_gemm = gemm_err = None
+    if rank == 0:
+        try:
+            gemm_ms, n_gemm = gemm_only_time(pkg, d, reps=50)
+        except Exception as e:
+            gemm_err = str(e)
+    barrier()
 
     # ---- e2e through the C-ABI with host buffers ----------------------------------------------
     # Every step: B fresh host rows -> pinned staging -> H2D into the ring (dqnb_add_transitions), one
@@ -461,7 +470,8 @@ def main():
         fpt = flop_per_transition(S, hidden)
         # dominant kernel: the layer GEMMs.  Timed live: all GEMM launches of one update, back to back.
         try:
-            gemm_ms, n_gemm = gemm_only_time(pkg, d, reps=50)
+            if gemm_ms is None:
+                raise RuntimeError(gemm_err or "GEMM-only replay not measured")
             traffic, traffic_src = ncu_traffic_per_launch()
             ach = fpt * B / (gemm_ms * 1e-3) / 1e12
             line["roofline"] = {

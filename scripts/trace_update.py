@@ -41,6 +41,10 @@ d.update(20)
 ms = d.benchmark(200)
 print(f"graph replay (tracing on): {ms/200*1e3:.1f} us per update")
 d.update(1)
+if os.environ.get("TRACE_GEMMS_ONLY"):      # timeline of bench.py's roofline leg: the update's GEMM launches back to back on one stream
+    import bench
+    ms, ng = bench.gemm_only_time(P, d, reps=3)
+    print(f"GEMM-only replay: {ng} launches, {ms*1e3:.1f} us per replay")
 buf = (C.c_longlong * 16384)()
 n = L.dqnb_debug_trace(d._h, buf, 16384)
 t = np.array(list(buf[:n]), dtype=np.int64).reshape(-1, 16)
