@@ -89,6 +89,11 @@ def check(P, dist, torch, rank, world, local, S, B, hidden, comm="p2p", n_update
             ok = False
 
     for u in range(n_updates):
+        if world > 1:
+            # rank 0 spends seconds in the oracle between updates (5 s at the wide shapes): the others wait for it HERE,
+            # on the host, not inside the exchange kernel, whose timeout is for peers that are gone
+            torch.cuda.synchronize()
+            dist.barrier()
         loss, avgq = d.update_with_indices(idx[u])
         mine = [np.ascontiguousarray(shard[k][idx[u]]) for k in range(6)]
         if world > 1:

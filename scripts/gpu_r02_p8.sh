@@ -1,7 +1,7 @@
 #!/bin/bash
 # 8-GPU box: data-parallel parity at the BASELINE shapes (cfg2 x8, cfg5 as specified), cfg4 with 8 ranks, the 8-GPU bench line
 mkdir -p gpurun_out
-export DQNB_P2P_TIMEOUT_MS=3000
+export DQNB_P2P_TIMEOUT_MS=10000
 nvidia-smi -L | wc -l
 timeout 500 python -m pytest tests/test_gpu_multi.py -x -q -m gpu -k "eight" > gpurun_out/r02p8_tests.log 2>&1
 echo "tests rc=$?"; tail -6 gpurun_out/r02p8_tests.log
