@@ -804,6 +804,7 @@ static void build_solver(dqnb_handle_s *h, int is_critic, const SegTable &segs, 
       ra.tab = h->p2p_tab; ra.world = h->cfg.world_size; ra.rank = h->cfg.rank; ra.net = is_critic; ra.flag_off = h->x_flag;
       ra.epoch = h->p2p_epoch; ra.flag_ticket = h->flag_ticket;
       x.count = g.flat + 4; x.epoch = h->p2p_epoch; x.ticket = h->p2p_ticket; x.err = h->p2p_err; x.err_dev = h->p2p_err_dev;
+      x.fence_all = env_int("DQNB_P2P_FENCE_ALL", 0);
       x.timeout_ns = (unsigned long long)std::max(1, env_int("DQNB_P2P_TIMEOUT_MS", 20000)) * 1000000ull;
       x.block_ss = h->p2p_block_ss;
       ar.blocks = 128;

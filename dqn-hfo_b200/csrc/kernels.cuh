@@ -584,10 +584,15 @@ __global__ void __launch_bounds__(256) reduce_kernel(const ReduceArgs a) {
     st->do_soft = (a.hp.soft_update_freq > 0 && mx % a.hp.soft_update_freq == 0) ? 1 : 0;
   }
   if (a.tab) {
+    // barrier, then ONE fence by the thread that takes the ticket (the grid-synchronisation pattern of cooperative
+    // groups: the barrier orders the block's stores before thread 0's fence, which is cumulative); a fence per thread cost
+    // the 750-block reduction 5 us
     __shared__ int s_last_blk;
-    __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) s_last_blk = (atomicAdd(a.flag_ticket + a.net, 1u) == gridDim.x - 1);
+    if (threadIdx.x == 0) {
+      __threadfence();
+      s_last_blk = (atomicAdd(a.flag_ticket + a.net, 1u) == gridDim.x - 1);
+    }
     __syncthreads();
     if (s_last_blk) {
       __threadfence();
@@ -627,9 +632,9 @@ struct AdamArgs {
   const int *comm_err;
 };
 __device__ __forceinline__ void adam_finalize(const AdamArgs &a, bool failed) {
-  __threadfence();
   __syncthreads();
   if (threadIdx.x != 0) return;
+  __threadfence();                  // after the barrier: cumulative over the block's stores (grid-sync pattern)
   const unsigned int done = atomicAdd(a.ticket, 1u);
   if (done != gridDim.x - 1) return;
   *a.ticket = 0;
@@ -754,6 +759,7 @@ struct P2PArgs {
   unsigned int *ticket;           // [2] per net, local memory
   int *err;                       // host-mapped, sticky: written on a timeout, read by the host only
   int *err_dev;                   // device-resident twin: what kernels read
+  int fence_all;                  // A/B knob DQNB_P2P_FENCE_ALL=1: every thread issues the system fence (round-1 behaviour)
   unsigned long long timeout_ns;
 };
 __device__ __forceinline__ bool spin_until_ge(const unsigned int *flag, unsigned int target, int *err, int *err_dev, unsigned long long timeout_ns) {
@@ -835,8 +841,13 @@ __global__ void __launch_bounds__(512) p2p_allreduce_kernel(const P2PArgs a) {
   }
   // C
   if (a.trace && blockIdx.x == 0 && threadIdx.x == 0) a.trace[4] = (long long)gtime_ns();
-  __threadfence_system();            // this block's remote stores are acknowledged (one NVLink round trip behind the data)
   __syncthreads();
+  if (threadIdx.x == 0) {
+    // one system fence per block, after the barrier (cumulative over the block's remote stores): they are acknowledged
+    // - one NVLink round trip behind the data - before the ticket
+    if (a.fence_all) ; else __threadfence_system();
+  }
+  if (a.fence_all) { __threadfence_system(); __syncthreads(); }
   if (a.trace && blockIdx.x == 0 && threadIdx.x == 0) a.trace[5] = (long long)gtime_ns();
   if (threadIdx.x == 0) {
     const unsigned int t = atomicAdd(a.ticket + a.net, 1u);

@@ -94,6 +94,8 @@ def main(total_workers=64, env_steps=160, S=58, B=256, hidden=(256, 128, 64, 64)
     warm = O.synth_batch(O.make_config(state_size=S, batch=warm_rows, hidden=hidden), rng, p_term=0.1)
     d.add_transitions(warm[0], warm[1], warm[2], warm[3], warm[5], warm[4])
     appended = warm_rows
+    if world > 1:                                            # start together: the first exchange should not have to wait for
+        torch.cuda.synchronize(); dist.barrier()             # a rank that is still initialising
     ocfg = O.make_config(state_size=S, batch=B, hidden=hidden)
     episodes = [[] for _ in range(W)]
     pending = 0                                              # sequence number of the last enqueued update
