@@ -1,9 +1,12 @@
 // host_selftest.cpp — CPU-only checks of the host mirror (no GPU, no libdqn_b200 calls): flag
 // parsing, GetAction semantics, LabelTransitions arithmetic, the in-process HFO stand-in and the
-// reward shaping of HFOGameState.  Exit code 0 = all checks passed.
+// reward shaping of HFOGameState; with --gpu, the checks that need a DQN object (SelectActions' epsilon branch and the
+// order of its random draws).  Exit code 0 = all checks passed.
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <memory>
+#include <random>
 #include <string>
 #include <vector>
 
@@ -25,7 +28,70 @@ using dqn::FLAGS_hidden;
 static int failures = 0;
 #define EXPECT(c) do { if (!(c)) { std::fprintf(stderr, "FAIL %s:%d: %s\n", __FILE__, __LINE__, #c); ++failures; } } while (0)
 
-int main() {
+// --gpu: the part of the mirror that needs a device.  SelectActions' epsilon branch (dqn.cpp:695-711) and
+// GetRandomActorOutput (dqn.cpp:664-682) draw from the DQN's std::mt19937 in a fixed order - one double for the coin flip,
+// then per row 4 logits U(-1,1), dash power U(-100,100), three angles U(-180,180), kick power U(0,100), kick angle - and the
+// greedy branch consumes exactly the coin flip.  Replayed here on a second engine with the same seed: bit equality.
+static void gpu_section() {
+  shim::set_flag("seed", "7"); shim::set_flag("batch_size", "32"); shim::set_flag("hidden", "64,32,32,16"); shim::set_flag("memory", "1000");
+  const int S = 59;
+  caffe::SolverParameter ap, cp;
+  ap.set_type("Adam"); cp.set_type("Adam");
+  ap.set_base_lr(1e-5f); cp.set_base_lr(1e-3f);
+  ap.set_momentum(0.95f); cp.set_momentum(0.95f); ap.set_momentum2(0.999f); cp.set_momentum2(0.999f);
+  ap.set_clip_gradients(10.f); cp.set_clip_gradients(10.f);
+  ap.net_param_ = dqn::CreateActorNet(S); cp.net_param_ = dqn::CreateCriticNet(S);
+  dqn::DQN d(ap, cp, "/tmp/host_selftest_gpu", S, 0);
+  std::mt19937 twin(7);
+  auto U = [&](float lo, float hi) { return std::uniform_real_distribution<float>(lo, hi)(twin); };
+  std::vector<dqn::InputStates> batch;
+  std::mt19937 srng(11);
+  for (int i = 0; i < 5; ++i) {
+    auto st = std::make_shared<std::vector<float>>(S);
+    for (float &v : *st) v = std::uniform_real_distribution<float>(-1.f, 1.f)(srng);
+    dqn::InputStates in; in[dqn::kStateInputCount - 1] = st;
+    batch.push_back(in);
+  }
+  // epsilon = 1: the whole batch is random, rows drawn one after the other
+  std::vector<dqn::ActorOutput> r = d.SelectActions(batch, 1.0);
+  (void)std::uniform_real_distribution<double>(0.0, 1.0)(twin);          // the coin flip
+  EXPECT(r.size() == batch.size());
+  for (auto &o : r) {
+    for (int k = 0; k < 4; ++k) EXPECT(o[k] == U(-1.f, 1.f));
+    EXPECT(o[4] == U(-100.f, 100.f)); EXPECT(o[5] == U(-180.f, 180.f)); EXPECT(o[6] == U(-180.f, 180.f));
+    EXPECT(o[7] == U(-180.f, 180.f)); EXPECT(o[8] == U(0.f, 100.f)); EXPECT(o[9] == U(-180.f, 180.f));
+    EXPECT(o[8] >= 0.f && o[8] <= 100.f && std::fabs(o[4]) <= 100.f);
+  }
+  // epsilon = 0: greedy, consumes only the coin flip; deterministic; the same rows give the same actions one by one
+  std::vector<dqn::ActorOutput> g1 = d.SelectActions(batch, 0.0);
+  (void)std::uniform_real_distribution<double>(0.0, 1.0)(twin);
+  std::vector<dqn::ActorOutput> g2 = d.SelectActions(batch, 0.0);
+  (void)std::uniform_real_distribution<double>(0.0, 1.0)(twin);
+  EXPECT(g1 == g2);
+  dqn::ActorOutput one = d.SelectAction(batch[3], 0.0);
+  (void)std::uniform_real_distribution<double>(0.0, 1.0)(twin);
+  for (int k = 0; k < 10; ++k) EXPECT(std::fabs(one[k] - g1[3][k]) <= 1e-6f * (1.f + std::fabs(one[k])));
+  // the engines are still in step: the next random output matches draw for draw
+  dqn::ActorOutput nxt = d.GetRandomActorOutput();
+  for (int k = 0; k < 4; ++k) EXPECT(nxt[k] == U(-1.f, 1.f));
+  EXPECT(nxt[4] == U(-100.f, 100.f));
+  // 0 < epsilon < 1: the branch taken is the coin flip's
+  for (int t = 0; t < 20; ++t) {
+    std::mt19937 peek(twin);                                                   // a copy: look at the coin without consuming it
+    const bool expect_random = std::uniform_real_distribution<double>(0.0, 1.0)(peek) < 0.5;
+    std::vector<dqn::ActorOutput> m = d.SelectActions(batch, 0.5);
+    (void)std::uniform_real_distribution<double>(0.0, 1.0)(twin);
+    if (expect_random) { for (auto &o : m) { for (int k = 0; k < 4; ++k) EXPECT(o[k] == U(-1.f, 1.f)); for (int k = 4; k < 10; ++k) (void)U(k == 4 ? -100.f : k == 8 ? 0.f : -180.f, k == 4 || k == 8 ? 100.f : 180.f); } }
+    else EXPECT(m == g1);
+  }
+}
+
+int main(int argc, char **argv) {
+  if (argc > 1 && std::string(argv[1]) == "--gpu") {
+    gpu_section();
+    std::printf(failures ? "host_selftest --gpu: %d FAILURES\n" : "host_selftest --gpu: ok\n", failures);
+    return failures ? 1 : 0;
+  }
   {  // flags
     const char *av[] = {"prog", "-gamma=0.5", "--batch_size", "1024", "-hidden=64,32", "positional"};
     int ac = 6; char **a = const_cast<char **>(av);

@@ -68,6 +68,15 @@ def test_host_headers_keep_the_reference_api_surface():
 
 
 @pytest.mark.gpu
+def test_select_actions_epsilon_branch_and_draw_order():
+    """SelectActions' coin flip, GetRandomActorOutput's ten draws per row in the reference's order, the greedy
+    branch consuming exactly one draw - replayed on a twin std::mt19937 (host_selftest --gpu)."""
+    build_host()
+    out = subprocess.run([os.path.join(HOST, "host_selftest"), "--gpu"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "host_selftest --gpu: ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+@pytest.mark.gpu
 def test_dqn_main_benchmark_train_snapshot_resume(tmp_path):
     build_host()
     exe = os.path.join(HOST, "dqn")
