@@ -13,6 +13,6 @@ for tool in memcheck racecheck synccheck; do
   echo "rc=$? $(grep -c 'ERROR SUMMARY' gpurun_out/sanitize_${tool}_smoke.log) summaries"; tail -2 gpurun_out/sanitize_${tool}_smoke.log
 done
 echo "== memcheck: gemm unit tests (tile / ring variants)"
-timeout 600 compute-sanitizer --tool memcheck --error-exitcode 7 python -m pytest tests/test_gpu_gemm.py -x -q -m gpu -k "tile_and_ring or exact" \
+timeout 600 compute-sanitizer --tool memcheck --error-exitcode 7 python -m pytest tests/test_gpu_gemm.py -x -q -m gpu -k "tile_and_ring or exact or tensor_memory" \
   > gpurun_out/sanitize_memcheck_gemm.log 2>&1
 echo "rc=$?"; tail -3 gpurun_out/sanitize_memcheck_gemm.log
