@@ -74,7 +74,8 @@ static void gpu_section() {
   // the engines are still in step: the next random output matches draw for draw
   dqn::ActorOutput nxt = d.GetRandomActorOutput();
   for (int k = 0; k < 4; ++k) EXPECT(nxt[k] == U(-1.f, 1.f));
-  EXPECT(nxt[4] == U(-100.f, 100.f));
+  EXPECT(nxt[4] == U(-100.f, 100.f)); EXPECT(nxt[5] == U(-180.f, 180.f)); EXPECT(nxt[6] == U(-180.f, 180.f));
+  EXPECT(nxt[7] == U(-180.f, 180.f)); EXPECT(nxt[8] == U(0.f, 100.f)); EXPECT(nxt[9] == U(-180.f, 180.f));
   // 0 < epsilon < 1: the branch taken is the coin flip's
   for (int t = 0; t < 20; ++t) {
     std::mt19937 peek(twin);                                                   // a copy: look at the coin without consuming it
