@@ -232,6 +232,7 @@ DQN::DQN(caffe::SolverParameter &actor_solver_param, caffe::SolverParameter &cri
 DQN::~DQN() {
   if (share_) {          // leave the sharing group: the others must not write through into a dead handle
     std::lock_guard<std::mutex> lock(share_->mu);
+    std::lock_guard<std::recursive_mutex> self(mu_);
     auto &m = share_->members;
     m.erase(std::remove(m.begin(), m.end(), this), m.end());
   }
@@ -241,6 +242,8 @@ DQN::~DQN() {
 
 // -async_update: the loss of the last enqueued update has not been looked at yet (dqn.cpp:906 checks every one)
 void DQN::drain_pending() {
+  std::lock_guard<std::recursive_mutex> self(mu_);
+
   if (pending_step_ <= 0) return;
   float loss = 0.f, avg_q = 0.f;
   DQNB_OK(dqnb_results(h_, pending_step_, 1, &loss, &avg_q));
@@ -249,6 +252,8 @@ void DQN::drain_pending() {
 }
 
 void DQN::refresh_iters() const {
+  std::lock_guard<std::recursive_mutex> self(mu_);
+
   if (!iters_dirty_) return;
   int32_t a = 0, c = 0;
   DQNB_OK(dqnb_iters(h_, &a, &c));
@@ -256,10 +261,12 @@ void DQN::refresh_iters() const {
 }
 int DQN::critic_iter() const { refresh_iters(); return critic_iter_cache_; }
 int DQN::actor_iter() const { refresh_iters(); return actor_iter_cache_; }
-int DQN::memory_size() const { return dqnb_memory_size(h_); }
-void DQN::ClearReplayMemory() { DQNB_OK(dqnb_clear_memory(h_)); }
+int DQN::memory_size() const { std::lock_guard<std::recursive_mutex> self(mu_); return dqnb_memory_size(h_); }
+void DQN::ClearReplayMemory() { std::lock_guard<std::recursive_mutex> self(mu_); DQNB_OK(dqnb_clear_memory(h_)); }
 
-void DQN::Benchmark(int iterations) {  // dqn.cpp:487-498
+void DQN::Benchmark(int iterations) {
+  std::lock_guard<std::recursive_mutex> self(mu_);
+  // dqn.cpp:487-498
   LOG(INFO) << "*** Benchmark begins ***";
   drain_pending();
   float ms = 0.f;
@@ -288,6 +295,8 @@ ActorOutput DQN::SelectAction(const InputStates &last_states, const double epsil
 }
 
 std::vector<ActorOutput> DQN::SelectActions(const std::vector<InputStates> &states_batch, const double epsilon) {
+  std::lock_guard<std::recursive_mutex> self(mu_);
+
   CHECK(epsilon >= 0.0 && epsilon <= 1.0);
   CHECK_LE((int)states_batch.size(), batch_size_);
   std::vector<ActorOutput> out(states_batch.size());
@@ -308,7 +317,9 @@ std::vector<ActorOutput> DQN::SelectActions(const std::vector<InputStates> &stat
   return out;
 }
 
-float DQN::EvaluateAction(const InputStates &input_states, const ActorOutput &action) {  // dqn.cpp:688-693
+float DQN::EvaluateAction(const InputStates &input_states, const ActorOutput &action) {
+  std::lock_guard<std::recursive_mutex> self(mu_);
+  // dqn.cpp:688-693
   float q = 0.f;
   DQNB_OK(dqnb_evaluate(h_, 1, input_states[kStateInputCount - 1]->data(), action.data(), &q));
   return q;
@@ -316,12 +327,16 @@ float DQN::EvaluateAction(const InputStates &input_states, const ActorOutput &ac
 
 // ---- replay memory ------------------------------------------------------------------------------
 void DQN::AddTransition(const Transition &t) {
+  std::lock_guard<std::recursive_mutex> self(mu_);
+
   const auto &next = std::get<4>(t);
   DQNB_OK(dqnb_add_transition(h_, std::get<0>(t)[kStateInputCount - 1]->data(), std::get<1>(t).data(), std::get<2>(t),
                               std::get<3>(t), next ? (*next)->data() : nullptr, next ? 0 : 1));
 }
 
 void DQN::AddTransitions(const std::vector<Transition> &ts) {
+  std::lock_guard<std::recursive_mutex> self(mu_);
+
   const int n = (int)ts.size();
   if (n == 0) return;
   std::vector<float> s((size_t)n * state_size_), sn((size_t)n * state_size_, 0.f), a((size_t)n * 10), r(n), mc(n);
@@ -358,6 +373,8 @@ std::vector<int> DQN::SampleTransitionsFromMemory(int n) {  // dqn.cpp:501-509
 }
 
 std::pair<float, float> DQN::UpdateActorCritic() {
+  std::lock_guard<std::recursive_mutex> self(mu_);
+
   float loss = 0.f, avg_q = 0.f;
   if (FLAGS_async_update && !FLAGS_host_sampling) {
     long long step = 0;
@@ -383,12 +400,21 @@ std::pair<float, float> DQN::UpdateActorCritic() {
 
 void DQN::Update() {  // dqn.cpp:799-826
   if (memory_size() < FLAGS_memory_threshold) return;
-  if (share_) {          // multi-agent sharing: one member updates at a time, then its shared layers reach the others
-    std::lock_guard<std::mutex> lock(share_->mu);
+  std::shared_ptr<ShareGroup> grp;
+  { std::lock_guard<std::recursive_mutex> self(mu_); grp = share_; }   // thread 0 may be attaching us to its group right now
+  if (grp) {             // multi-agent sharing: one member updates at a time, then its shared layers reach the others
+    // lock order: the group, then this object, then one teammate at a time (a teammate that is acting holds only its
+    // own mutex, for the length of one call)
+    std::lock_guard<std::mutex> lock(grp->mu);
+    std::lock_guard<std::recursive_mutex> self(mu_);
     last_update_ = UpdateActorCritic();
     drain_pending();
-    for (DQN *m : share_->members)
-      if (m != this) DQNB_OK(dqnb_copy_shared_layers(m->h_, h_, share_->n_actor, share_->n_critic));
+    for (DQN *m : grp->members)
+      if (m != this) {
+        std::lock_guard<std::recursive_mutex> mate(m->mu_);
+        m->drain_pending();
+        DQNB_OK(dqnb_copy_shared_layers(m->h_, h_, grp->n_actor, grp->n_critic));
+      }
   } else
   last_update_ = UpdateActorCritic();
   if (critic_iter() % FLAGS_loss_display_iter == 0) {
@@ -451,6 +477,8 @@ static void write_file(const std::string &f, const std::string &bytes) {
 }
 
 void DQN::snapshot_net(int net, const std::string &base) const {
+  std::lock_guard<std::recursive_mutex> self(mu_);
+
   const int64_t n = dqnb_param_count(h_, net);
   std::vector<float> w((size_t)n), m((size_t)n), v((size_t)n);
   int32_t iter = 0;
@@ -473,6 +501,8 @@ void DQN::snapshot_net(int net, const std::string &base) const {
 // Net::CopyTrainedLayersFrom (dqn.cpp:529,:537): this build's flat file, or a Caffe NetParameter whose layers are
 // matched by name (layers the net does not have are ignored, layers the file does not have keep their weights)
 void DQN::load_weights(int net, const std::string &f) {
+  std::lock_guard<std::recursive_mutex> self(mu_);
+
   const std::string bytes = read_file(f);
   const int64_t n = dqnb_param_count(h_, net);
   std::vector<float> w((size_t)n);
@@ -498,7 +528,9 @@ void DQN::load_weights(int net, const std::string &f) {
 
 void DQN::Snapshot() { Snapshot(save_path_, FLAGS_remove_old_snapshots, FLAGS_snapshot_memory); }
 
-void DQN::Snapshot(const std::string &prefix, bool remove_old, bool snapshot_memory) {  // dqn.cpp:586-620
+void DQN::Snapshot(const std::string &prefix, bool remove_old, bool snapshot_memory) {
+  std::lock_guard<std::recursive_mutex> self(mu_);
+  // dqn.cpp:586-620
   drain_pending();
   const int ai = actor_iter(), ci = critic_iter();
   snapshot_net(DQNB_ACTOR, prefix + "_actor_iter_" + std::to_string(ai));
@@ -522,6 +554,8 @@ void DQN::LoadCriticWeights(const std::string &f) { load_weights(DQNB_CRITIC, f)
 
 // Solver::Restore (dqn.cpp:541-557): iteration + Adam history, weights from the model the state points to
 void DQN::restore_solver(int net, const std::string &f) {
+  std::lock_guard<std::recursive_mutex> self(mu_);
+
   const std::string bytes = read_file(f);
   const int64_t n = dqnb_param_count(h_, net);
   if (bytes.size() >= 8 && std::memcmp(bytes.data(), "DQNBS001", 8) == 0) {
@@ -562,6 +596,8 @@ void DQN::RestoreCriticSolver(const std::string &f) {
 //   int32 n, then per transition  state[S] f32 | ActorOutput 10 f32 | reward f32 | on_policy_target f32 | terminal u8
 // with the next state implicit = the following record's state unless terminal (dqn.cpp:1218-1220).
 void DQN::SnapshotReplayMemory(const std::string &filename) {
+  std::lock_guard<std::recursive_mutex> self(mu_);
+
   gzFile out = gzopen(filename.c_str(), "wb");
   CHECK(out != nullptr) << "cannot write " << filename;
   const int n = memory_size();
@@ -588,6 +624,8 @@ void DQN::SnapshotReplayMemory(const std::string &filename) {
 }
 
 void DQN::LoadReplayMemory(const std::string &filename) {
+  std::lock_guard<std::recursive_mutex> self(mu_);
+
   CHECK(is_regular_file(filename)) << "Invalid file: " << filename;
   LOG(INFO) << "Loading replay memory from " << filename;
   ClearReplayMemory();
@@ -653,6 +691,8 @@ void DQN::ShareParameters(DQN &other, int num_actor_layers_to_share, int num_cri
     LOG(INFO) << "Sharing Actor Layer " << (i < (int)hidden_.size() ? "ip" + std::to_string(i + 1) + "_layer" : std::string(kActorNames[i - hidden_.size()]));
   for (int i = 0; i < num_critic_layers_to_share; ++i)
     LOG(INFO) << "Sharing Critic Layer " << (i < (int)hidden_.size() ? "ip" + std::to_string(i + 1) + "_layer" : std::string("q_values_layer"));
+  std::lock_guard<std::recursive_mutex> self(mu_);
+  std::lock_guard<std::recursive_mutex> mate(other.mu_);     // the teammate's thread may already be playing
   drain_pending();
   other.drain_pending();
   DQNB_OK(dqnb_copy_shared_layers(other.h_, h_, num_actor_layers_to_share, num_critic_layers_to_share));
@@ -664,6 +704,11 @@ void DQN::ShareParameters(DQN &other, int num_actor_layers_to_share, int num_cri
 void DQN::ShareReplayMemory(DQN &other) {
   CHECK(&other != this);
   CHECK_EQ(state_size_, other.state_size_);
+  std::shared_ptr<ShareGroup> grp = share_;               // a group's updates reach into teammates too: same lock order
+  std::unique_lock<std::mutex> glock;
+  if (grp) glock = std::unique_lock<std::mutex>(grp->mu);
+  std::lock_guard<std::recursive_mutex> self(mu_);
+  std::lock_guard<std::recursive_mutex> mate(other.mu_);
   other.ClearReplayMemory();
   const int n = memory_size(), S = state_size_, chunk = 16384;
   std::vector<float> s((size_t)chunk * S), sn((size_t)chunk * S), a((size_t)chunk * (kActionSize + kActionParamSize)), r(chunk), mc(chunk);

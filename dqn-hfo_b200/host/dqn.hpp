@@ -141,6 +141,11 @@ class DQN {
   // (ShareData aliases memory upstream; here the member that just updated writes its shared layers through to the others)
   struct ShareGroup;
   std::shared_ptr<ShareGroup> share_;
+  // A handle is thread-compatible, not thread-safe (like a Caffe net).  Upstream every DQN is used by its own agent
+  // thread only - except that thread 0 reaches into its teammates' objects to share layers / replay memory while they
+  // are already playing (dqn_main.cpp:305-323) and, here, a member's update writes its shared layers into the others'
+  // handles.  Every method that touches the handle therefore holds the object's mutex (recursive: Update -> Snapshot).
+  mutable std::recursive_mutex mu_;
   long long pending_step_ = 0;   // -async_update: sequence number of the update whose results are still to be read
 };
 
