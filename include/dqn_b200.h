@@ -135,8 +135,8 @@ int dqnb_update_with_indices(dqnb_handle h, const int32_t *idx, float *critic_lo
 /* Same as dqnb_update but returns the device time of the n updates measured with CUDA events on
  * the handle's stream (the reference's Benchmark(), dqn.cpp:487-498). */
 int dqnb_benchmark(dqnb_handle h, int32_t n_updates, float *elapsed_ms);
-/* Device time (CUDA events) of just the dense-layer launches of one update, averaged over reps:
- * the live measurement behind bench.py's roofline line.  Leaves learner state untouched except
+/* Device time (CUDA events) of just the dense-layer launches of one update, replayed back to back as a captured graph
+ * and averaged over reps: the live measurement behind bench.py's roofline line.  Leaves learner state untouched except
  * for scratch activations. */
 int dqnb_benchmark_gemms(dqnb_handle h, int32_t reps, float *ms_per_update, int32_t *gemm_launches);
 /* Draws the indices the next dqnb_update would use, without updating (tests). */
@@ -146,15 +146,20 @@ int dqnb_peek_sample_indices(dqnb_handle h, int32_t *idx);
  * The epsilon coin flip of SelectActions (dqn.cpp:695-711) stays in the host wrapper so that the
  * host RNG stream is the reference's. */
 int dqnb_select_actions(dqnb_handle h, int32_t n, const float *states, float *out10);
-/* Split form for overlapping rollouts with learning: enqueue on the act stream, then wait. */
+/* 1..64 rows never wait for the learner: the call runs a captured graph of skinny-M kernels on the handle's ACT stream,
+ * reading a snapshot of the actor that the optimiser publishes at the end of every update, with rows and completion
+ * travelling through host-mapped memory (csrc/kernels.cuh act_layer_kernel).  More rows (up to max_act_batch) use the
+ * tcgen05 layer kernels on the learner's stream.
+ * Split form for overlapping the caller's own work: enqueue, then wait. */
 int dqnb_select_actions_async(dqnb_handle h, int32_t n, const float *states);
 int dqnb_select_actions_wait(dqnb_handle h, int32_t n, float *out10);
 /* CriticForward (dqn.cpp:982-1020) / EvaluateAction (dqn.cpp:688-693): q [n]. */
 int dqnb_evaluate(dqnb_handle h, int32_t n, const float *states, const float *act10, float *q);
 
-/* Data-parallel replicas: one process per GPU; gradients are summed with ncclAllReduce on the
- * handle's stream after each backward (no counterpart in the reference).
- * id128 is an ncclUniqueId obtained on rank 0 and broadcast by the caller. */
+/* Data-parallel replicas: one process per GPU, config.world_size / config.rank (no counterpart in the reference,
+ * SURVEY 8e).  Two ways to sum the gradients after each backward pass; the product path is the peer-memory exchange
+ * below.  VALIDATION ALTERNATIVE: ncclAllReduce on the handle's stream; id128 is an ncclUniqueId obtained on rank 0 and
+ * broadcast by the caller (same results bit for bit, slower). */
 int dqnb_comm_unique_id(void *id128);
 int dqnb_comm_init(dqnb_handle h, const void *id128);
 /* Product path for the gradient exchange: a fused reduce-scatter + all-gather kernel over NVLink peer
@@ -163,7 +168,9 @@ int dqnb_comm_init(dqnb_handle h, const void *id128);
  * every rank maps them.  Selecting either exchange rebuilds the captured update graph. */
 int dqnb_comm_p2p_handle(dqnb_handle h, void *handle64);
 int dqnb_comm_p2p_init(dqnb_handle h, const void *handles /* world_size x 64 bytes */);
-/* 0 = healthy; 1 = a peer missed the exchange kernel's 2 s timeout (state is no longer valid). */
+/* 0 = healthy; 1 = a peer missed the exchange kernel's timeout (DQNB_P2P_TIMEOUT_MS, default 20 s).  The flag is sticky:
+ * from then on the optimiser kernels leave parameters, moments and iteration counters as they are, results read NaN, and
+ * dqnb_update / dqnb_update_with_indices / dqnb_results return -1 with a message. */
 int dqnb_comm_status(dqnb_handle h);
 
 /* Blocks until all work queued on the handle has finished. */
