@@ -231,7 +231,7 @@ struct SplitMat {           // [2][rows][ld] fp32 in HBM
 };
 
 struct Op {                 // one kernel launch of the update / act sequence
-  enum Kind { GEMM, GEMM_GROUP_UNUSED, GATHER, SAMPLE, HEAD_FWD, CRITIC_HEAD, ACTOR_HEAD_BWD, HEAD_BWD_W, COLSUM, REDUCE,
+  enum Kind { GEMM, GATHER, SAMPLE, HEAD_FWD, CRITIC_HEAD, ACTOR_HEAD_BWD, HEAD_BWD_W, COLSUM, REDUCE,
               ALLREDUCE, P2P_ALLREDUCE, ADAM, PREP, FINALIZE, FORK, JOIN, ACT_STAGE, ACT_LAYER } kind;
   int branch = 0;           // 0 = main stream; 1, 2 = side streams between FORK and JOIN
   int wait_ev = -1;         // event the op's stream waits for before the launch (cross-branch edge)
@@ -392,17 +392,11 @@ struct Tuning {
                     //    pass instead of beside the target critic, which then runs alone with cluster split-K
   int cluster_b;    // 1: cluster split-K also for the target chains, which share the machine with the side chains
   int pdl_early;    // GEMM kernels: 1 = launch_dependents right after the wait, 0 = after the last MMA issue
-  int store_wait_full;   // GEMM epilogue: 1 = cp.async.bulk.wait_group (stores written), 0 = .read (staging released)
   int side_delay;   // 1: a side chain of the forward phase starts when the critical chain's first (machine-filling) layer
                     //    of the same pair has finished, and the actor's chain joins only before its consumer
-  int bn_big;       // 128: dX / dW GEMMs that fill the machine with 128x64 tiles anyway use 128x128 tiles (half the CTAs,
-                    //      1.6x the tensor rate per CTA), so the two big GEMMs of a backward pass run side by side
   int bn_fwd, bn_fwd_side, bn_dx, bn_dw;   // N tile (64 / 128) per GEMM class
   int ts_min_kb;        // forward / dX GEMMs with at least this many k-blocks per CTA run in A-in-TMEM mode (0 < x; 9999 = never)
   int bn32_max_tiles;   // forward / dX GEMMs with at most this many 128x64 output tiles use 128x32 tiles instead
-  int bn32_cluster;     // 1: such GEMMs may still split K over a 2-CTA cluster
-  int dw_big_max_ctas;  // CTA budget of the split-K choice for the big weight-gradient GEMMs (>= 32 output tiles)
-  int dw_after_dx;  // bit l: the weight-gradient GEMM of tower layer l waits for the end of the dX chain (dZ[0])
   int bn_side_l1;   // N tile of a side chain's first layer: 128 halves its CTA count (128 -> 64), so that it fits beside
                     // the critical chain's second layer (64 CTAs) instead of queueing in front of it
   int st_fwd, st_fwd_side, st_dx, st_dw;   // smem ring depth per GEMM class (0 = deepest that fits)
@@ -414,16 +408,11 @@ struct Tuning {
     actor_late = env_int("DQNB_ACTOR_LATE", 0);
     cluster_b = env_int("DQNB_CLUSTER_B", 0);
     pdl_early = env_int("DQNB_PDL_EARLY", 0);
-    store_wait_full = env_int("DQNB_STORE_WAIT_FULL", 0);
     side_delay = env_int("DQNB_SIDE_DELAY", 1);
-    bn_big = env_int("DQNB_BN_BIG", 64);
     bn_fwd = env_int("DQNB_BN_FWD", 64);
     bn_fwd_side = env_int("DQNB_BN_FWD_SIDE", 64);
     ts_min_kb = env_int("DQNB_TS_MIN_KB", 8);
     bn32_max_tiles = env_int("DQNB_BN32_MAX_TILES", 32);
-    bn32_cluster = env_int("DQNB_BN32_CLUSTER", 0);
-    dw_big_max_ctas = env_int("DQNB_DW_BIG_MAX_CTAS", 160);
-    dw_after_dx = env_int("DQNB_DW_AFTER_DX", 0);
     bn_side_l1 = env_int("DQNB_BN_SIDE_L1", 128);
     bn_dx = env_int("DQNB_BN_DX", 64);
     bn_dw = env_int("DQNB_BN_DW", 128);   // 128-wide tiles, twice the splits: half the mainloop per CTA in the tail of a pass
@@ -442,9 +431,9 @@ static const Tuning &tuning() {
 // ---------------------------------------------------------------------------------------------
 // GEMM op builders
 // ---------------------------------------------------------------------------------------------
-static int pick_splits(int tiles, int kblocks, int max_splits, int max_ctas = 160) {
+static int pick_splits(int tiles, int kblocks, int max_splits) {
   int s = 1;
-  while (s * 2 <= max_splits && tiles * s * 2 <= max_ctas && kblocks / (s * 2) >= 2) s *= 2;
+  while (s * 2 <= max_splits && tiles * s * 2 <= 160 && kblocks / (s * 2) >= 2) s *= 2;
   return s;
 }
 
@@ -463,16 +452,13 @@ static int finish_gemm(const dqnb_config &cfg, Op *op) {
         ((p.M + BM - 1) / BM) * ((p.N + 63) / 64) <= tuning().bn32_max_tiles) { p.bn = 32; narrow = true; }
     if (p.stages < 2 || p.stages > tc_max_stages(p.bn)) p.stages = tc_max_stages(p.bn);
     p.pdl_early = tuning().pdl_early;
-    p.store_wait_full = tuning().store_wait_full;
     if (p.epi == EPI_DX && !p.relu_bits_in) DQNB_FAIL("EPI_DX needs the sign bits of the saved activation");
     // Forward / dX GEMMs with a long contraction but few output tiles: split K over a 2-CTA cluster
     // (DSMEM reduction in the epilogue) so that the dependent chain sees half the mainloop latency.
     {
       const int tiles = ((p.M + BM - 1) / BM) * ((p.N + p.bn - 1) / p.bn);
-      const bool no_cluster = p.cluster_k < 0;
-      p.cluster_k = 0;
-      if (!no_cluster && p.epi != EPI_PLAIN && p.splits == 1 && p.K / BK >= 16 && 2 * tiles <= 148 && cfg.use_graph >= 0 &&
-          (!narrow || tuning().bn32_cluster) &&
+      if (p.epi != EPI_PLAIN && p.splits == 1 && p.K / BK >= 16 && 2 * tiles <= 148 && cfg.use_graph >= 0 &&
+          !narrow &&
           !getenv("DQNB_NO_CLUSTER_SPLITK")) {
         p.cluster_k = 1;
         p.splits = 2;
@@ -518,7 +504,6 @@ static int op_dx(const dqnb_config &cfg, const NetGeom &g, int l, const float *P
   memset(&p, 0, sizeof(p));
   p.bn = (tuning().bn_dx == 128 && L.Kp % 128 == 0) ? 128 : 64;
   p.stages = tuning().st_dx;
-  if (tuning().bn_big == 128 && L.Kp % 128 == 0 && ((dZl.rows + BM - 1) / BM) * (L.Kp / 64) >= 128) { p.bn = 128; p.stages = 0; p.cluster_k = -1; }
   p.M = dZl.rows; p.N = L.Kp; p.K = L.Np; p.a_mn = 0; p.b_mn = 1; p.splits = 1; p.epi = EPI_DX;
   p.A = dZl.p; p.a_plane = dZl.plane(); p.lda = dZl.ld;
   p.B = P + L.w_off; p.b_plane = g.flat; p.ldb = L.Kp;
@@ -552,9 +537,8 @@ static int op_dw(const dqnb_config &cfg, const NetGeom &g, int l, const SplitMat
   p.M = L.Np; p.N = L.Kp; p.K = dZl.rows; p.a_mn = 1; p.b_mn = 1; p.epi = EPI_PLAIN;
   p.bn = (tuning().bn_dw == 128 && L.Kp % 128 == 0) ? 128 : 64;
   p.stages = tuning().st_dw;
-  if (tuning().bn_big == 128 && L.Kp % 128 == 0 && ((L.Np + BM - 1) / BM) * (L.Kp / 64) >= 64) { p.bn = 128; p.stages = 0; }
   const int tiles = ((p.M + BM - 1) / BM) * ((p.N + p.bn - 1) / p.bn);
-  p.splits = pick_splits(tiles, p.K / BK, kGradSplits, tiles >= 32 ? tuning().dw_big_max_ctas : 160);
+  p.splits = pick_splits(tiles, p.K / BK, kGradSplits);
   *splits_out = p.splits;
   p.A = dZl.p; p.a_plane = dZl.plane(); p.lda = dZl.ld;
   p.B = Xin.p; p.b_plane = Xin.plane(); p.ldb = Xin.ld;
@@ -613,7 +597,6 @@ static int launch_op(dqnb_handle_s *h, const Op &op, cudaStream_t s) {
       else
         e = launch_k(gemm_simt_kernel, op.grid, dim3(256), 0, s, op.gemm.p);
       break;
-    case Op::GEMM_GROUP_UNUSED: break;
     case Op::GATHER: e = launch_k(gather_kernel, dim3(h->Bp), dim3(128), 0, s, op.gather); break;
     case Op::SAMPLE: break;
     case Op::HEAD_FWD: e = launch_k(head_fwd_kernel, dim3(op.blocks), dim3(256), 0, s, op.head); break;
@@ -730,7 +713,6 @@ static int build_backward(dqnb_handle_s *h, const NetGeom &g, const float *P, co
     Op f; f.kind = Op::FORK; f.mask = fork_mask; ops.push_back(f);
     if (head_bwd_w) { Op w = *head_bwd_w; w.branch = 2; ops.push_back(w); }
   }
-  std::vector<Op> deferred;
   for (int l = top; l >= 0; --l) {
     if (want_dw) {
       Op op;
@@ -738,18 +720,14 @@ static int build_backward(dqnb_handle_s *h, const NetGeom &g, const float *P, co
       if (op_dw(h->cfg, g, l, h->dZ[l], l > 0 ? acts[l - 1] : X, h->Gpart[g.critic], h->gpart_stride[g.critic], &splits, &op)) return -1;
       op.branch = 3 + l;
       if (l < top) op.wait_ev = l;                              // dZ[l] is produced by the dX op below
-      // the big weight-gradient GEMMs of the middle layers become ready while the dX chain (critical path) still
-      // needs the whole machine for its widest layers; a CTA that is resident is never preempted, so they are held
-      // back until dZ[0] exists and then run beside the first layer's weight gradient (two CTAs per SM)
-      const bool held = l >= 1 && l < top && (tuning().dw_after_dx >> l & 1);
-      if (held) { op.wait_ev = 0; deferred.push_back(op); } else ops.push_back(op);
+      ops.push_back(op);
       const bool fused_here = fuse_cs && l < top;
       if (!fused_here) {
         // bias column sums of dZ[l] by a launch of their own: behind the weight gradient that waits for the same dZ;
         // the last two (whose GEMMs form the tail of the pass) beside their GEMMs on branch 2, after the head gradient
         Op c = make_colsum(h, g, l, l + 1);
         if (l > 1 || l == top) c.branch = 3 + l; else { c.branch = 2; c.wait_ev = l; }
-        if (held && c.branch == 3 + l) deferred.push_back(c); else ops.push_back(c);   // stays behind its weight gradient
+        ops.push_back(c);
       }
       // segment table entries (internal flat order: W_l then b_l)
       SegTable &T = *segs;
@@ -765,7 +743,6 @@ static int build_backward(dqnb_handle_s *h, const NetGeom &g, const float *P, co
       if (want_dw) op.rec_ev = l - 1;                           // dZ[l-1] ready
       if (fuse_cs) { op.gemm.p.colsum_out = h->Bpart[g.critic] + h->boff[l - 1]; op.gemm.p.colsum_stride = h->bflat; }
       ops.push_back(op);
-      if (l == 1) { ops.insert(ops.end(), deferred.begin(), deferred.end()); deferred.clear(); }   // event 0 now exists
     }
   }
   if (want_dw) {
@@ -804,7 +781,6 @@ static void build_solver(dqnb_handle_s *h, int is_critic, const SegTable &segs, 
       ra.tab = h->p2p_tab; ra.world = h->cfg.world_size; ra.rank = h->cfg.rank; ra.net = is_critic; ra.flag_off = h->x_flag;
       ra.epoch = h->p2p_epoch; ra.flag_ticket = h->flag_ticket;
       x.count = g.flat + 4; x.epoch = h->p2p_epoch; x.ticket = h->p2p_ticket; x.err = h->p2p_err; x.err_dev = h->p2p_err_dev;
-      x.fence_all = env_int("DQNB_P2P_FENCE_ALL", 0);
       x.timeout_ns = (unsigned long long)std::max(1, env_int("DQNB_P2P_TIMEOUT_MS", 20000)) * 1000000ull;
       x.block_ss = h->p2p_block_ss;
       ar.blocks = 128;

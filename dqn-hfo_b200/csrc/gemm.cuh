@@ -56,7 +56,6 @@ struct GemmParams {
                                               //    the accumulator drain + epilogue (measured: profiles/r01c_*)
   int a_ts;                                   // 1 (K-major A only): the A tile is copied shared -> tensor memory by four mover
                                               // warps and tcgen05.mma reads it from there (see gemm_tc_body)
-  int store_wait_full;                        // 1: the epilogue waits for its TMA stores to be written, not just read (A/B knob)
   int dbg;                                    // perf experiments (gemm_test only): bit0 skip MMA, bit1 skip TMA
   long long *dbg_clk;                         // optional: MMA-thread clock64 stamps {start, issued, complete}
 };
@@ -251,7 +250,6 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 // .read: wait until the staged boxes have been READ out of shared memory (it may then be released); the writes
 // themselves complete before the grid does, which is what griddepcontrol.wait / stream order of the consumer wait for
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void st_smem_f4(uint32_t addr, float a, float b, float c, float d) {
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
@@ -737,7 +735,7 @@ __device__ __forceinline__ void gemm_tc_body(const GemmArgs &args, const int n_t
           p.colsum_out[(long long)m_tile * p.colsum_stride + n_base + threadIdx.x] = ((c[0] + c[BN_]) + c[2 * BN_]) + c[3 * BN_];
         }
       }
-      if (lane == 0) { if (p.store_wait_full) bulk_wait_all(); else bulk_wait_read(); }   // the boxes have been read before shared memory goes away
+      if (lane == 0) bulk_wait_read();         // the boxes have been read before shared memory goes away
       __syncwarp();
       if (warp == 2 && lane == 0) { DQNB_STAMP(5); DQNB_STAMP_MAX(10); }
     }

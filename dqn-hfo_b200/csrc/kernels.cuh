@@ -759,7 +759,6 @@ struct P2PArgs {
   unsigned int *ticket;           // [2] per net, local memory
   int *err;                       // host-mapped, sticky: written on a timeout, read by the host only
   int *err_dev;                   // device-resident twin: what kernels read
-  int fence_all;                  // A/B knob DQNB_P2P_FENCE_ALL=1: every thread issues the system fence (round-1 behaviour)
   unsigned long long timeout_ns;
 };
 __device__ __forceinline__ bool spin_until_ge(const unsigned int *flag, unsigned int target, int *err, int *err_dev, unsigned long long timeout_ns) {
@@ -845,9 +844,8 @@ __global__ void __launch_bounds__(512) p2p_allreduce_kernel(const P2PArgs a) {
   if (threadIdx.x == 0) {
     // one system fence per block, after the barrier (cumulative over the block's remote stores): they are acknowledged
     // - one NVLink round trip behind the data - before the ticket
-    if (a.fence_all) ; else __threadfence_system();
+    __threadfence_system();
   }
-  if (a.fence_all) { __threadfence_system(); __syncthreads(); }
   if (a.trace && blockIdx.x == 0 && threadIdx.x == 0) a.trace[5] = (long long)gtime_ns();
   if (threadIdx.x == 0) {
     const unsigned int t = atomicAdd(a.ticket + a.net, 1u);

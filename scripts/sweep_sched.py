@@ -10,7 +10,7 @@ from bench import synth_replay
 P = load_package()
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 s, a, r, mc, term, sn = synth_replay(65536, 58, 1)
-KEYS = ["DQNB_DW_BIG_MAX_CTAS", "DQNB_TS_MIN_KB", "DQNB_BN32_MAX_TILES", "DQNB_BN32_CLUSTER", "DQNB_DW_AFTER_DX", "DQNB_BN_SIDE_L1", "DQNB_STORE_WAIT_FULL", "DQNB_SIDE_DELAY", "DQNB_FUSE_COLSUM", "DQNB_FUSE_TL", "DQNB_ALIAS", "DQNB_ACTOR_LATE", "DQNB_GATHER_AHEAD", "DQNB_BN_BIG", "DQNB_PDL_EARLY", "DQNB_CLUSTER_B", "DQNB_ST_FWD", "DQNB_ST_FWD_SIDE", "DQNB_ST_DX", "DQNB_ST_DW", "DQNB_DW_STREAMS", "DQNB_SCHED", "DQNB_DW0_MAIN", "DQNB_COLSUM_SIDE", "DQNB_BN_FWD", "DQNB_BN_FWD_SIDE", "DQNB_BN_DX", "DQNB_BN_DW"]
+KEYS = ["DQNB_TS_MIN_KB", "DQNB_BN32_MAX_TILES", "DQNB_BN_SIDE_L1", "DQNB_SIDE_DELAY", "DQNB_FUSE_COLSUM", "DQNB_FUSE_TL", "DQNB_ACTOR_LATE", "DQNB_GATHER_AHEAD", "DQNB_PDL_EARLY", "DQNB_CLUSTER_B", "DQNB_ST_FWD", "DQNB_ST_FWD_SIDE", "DQNB_ST_DX", "DQNB_ST_DW", "DQNB_SCHED", "DQNB_BN_FWD", "DQNB_BN_FWD_SIDE", "DQNB_BN_DX", "DQNB_BN_DW"]
 
 def run(cfg):
     for k in KEYS:
