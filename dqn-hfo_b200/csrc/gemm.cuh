@@ -10,10 +10,13 @@
 //               below (mask from that layer's saved activation) -> split planes of dZ
 //   EPI_PLAIN : raw fp32 (weight-gradient partials of the split-K dW GEMMs, input diffs)
 //
-// gemm_tc_kernel   : TMA (cp.async.bulk.tensor.3d, 128B swizzle) -> 4-stage smem ring ->
-//                    tcgen05.mma.cta_group::1.kind::tf32 (M128 x N64 x K8, fp32 accumulators in
-//                    TMEM) -> tcgen05.ld epilogue.  Warp roles: 0 = TMA producer, 1 = MMA issuer
-//                    (+ TMEM alloc); all 8 warps run the epilogue (two per TMEM lane quarter).
+// gemm_tc_kernel   : TMA (cp.async.bulk.tensor.3d, 128B swizzle) -> 2-4-stage smem ring ->
+//                    tcgen05.mma.cta_group::1.kind::tf32, two instructions per K = 8 step (A_hi x [B_hi | B_lo] with
+//                    N = 2 BN, A_lo x B_hi with N = BN), three fp32 accumulators in TMEM, tiles M128 x N{32,64,128}
+//                    -> tcgen05.ld epilogue -> swizzled staging -> TMA store.  Warp roles: 0 = TMA producer,
+//                    1 = MMA issuer (+ TMEM alloc), 4-7 = A movers when the A operand is staged in tensor memory
+//                    (tcgen05.st); all 8 warps run the epilogue (two per TMEM lane quarter).  The epilogue flavour
+//                    is a template parameter.
 // gemm_simt_kernel : plain FFMA tiles over the same operands/epilogues (verification mode).
 #pragma once
 #include "common.cuh"

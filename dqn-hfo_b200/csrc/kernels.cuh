@@ -1,7 +1,8 @@
 // kernels.cuh — the non-GEMM kernels of one UpdateActorCritic (dqn.cpp:828-972): index sampling,
 // replay gather, linear heads, TD target / Euclidean loss, inverting gradients, bias gradients,
-// gradient reduction + global-norm clip, Adam + soft target update.  All HBM/L2-bound; loads are
-// coalesced along the contiguous (feature) axis and vectorised where the layout allows.
+// gradient reduction + global-norm clip, Adam + soft target update (+ the actor snapshot of the act path), the skinny-M
+// act-path kernels (SelectActionGreedily, dqn.cpp:734-766) and the multi-GPU gradient exchange over NVLink peer memory.
+// All HBM/L2/latency-bound; loads are coalesced along the contiguous (feature) axis and vectorised where the layout allows.
 #pragma once
 #include "common.cuh"
 
