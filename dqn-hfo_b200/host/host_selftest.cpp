@@ -4,6 +4,7 @@
 // order of its random draws).  Exit code 0 = all checks passed.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <random>
@@ -87,7 +88,38 @@ static void gpu_section() {
   }
 }
 
+// --write-caffemodel <out.caffemodel> <actor|critic> <state_size> <h1,h2,..> <weights.bin>
+// --read-caffemodel  <in.caffemodel>  <actor|critic> <state_size> <h1,h2,..> <weights_out.bin>
+// The checkpoint codec on its own (no GPU): flat learnable_params array (float32, Caffe order) <-> NetParameter file.
+// tests/test_caffemodel_opencv.py hands the written file to OpenCV's Caffe importer, a third-party reader of the format.
+static int caffemodel_tool(int argc, char **argv) {
+  if (argc != 7) { std::fprintf(stderr, "usage: %s --write-caffemodel|--read-caffemodel FILE actor|critic S H1,H2,.. WEIGHTS.bin\n", argv[0]); return 2; }
+  const bool write = std::string(argv[1]) == "--write-caffemodel", critic = std::string(argv[3]) == "critic";
+  const int S = std::atoi(argv[4]);
+  std::vector<int> hidden;
+  for (const char *c = argv[5]; *c;) { hidden.push_back(std::atoi(c)); while (*c && *c != ',') ++c; if (*c == ',') ++c; }
+  const long long n = caffe_proto::ParamCount(caffe_proto::ParamLayers(S, hidden, critic));
+  std::vector<float> flat((size_t)n, 0.f);
+  auto slurp = [](const char *f, std::string *out) { FILE *fp = std::fopen(f, "rb"); if (!fp) return false; char buf[1 << 16]; size_t k; while ((k = std::fread(buf, 1, sizeof(buf), fp)) > 0) out->append(buf, k); std::fclose(fp); return true; };
+  auto dump = [](const char *f, const void *p, size_t bytes) { FILE *fp = std::fopen(f, "wb"); if (!fp) return false; const bool ok = std::fwrite(p, 1, bytes, fp) == bytes; std::fclose(fp); return ok; };
+  if (write) {
+    std::string raw;
+    if (!slurp(argv[6], &raw) || (long long)raw.size() != 4 * n) { std::fprintf(stderr, "weights file: expected %lld floats\n", n); return 1; }
+    std::memcpy(flat.data(), raw.data(), raw.size());
+    const std::string bytes = caffe_proto::EncodeNet(caffe_proto::NetFromFlat(critic ? "Critic" : "Actor", S, hidden, critic, flat.data()));
+    return dump(argv[2], bytes.data(), bytes.size()) ? 0 : 1;
+  }
+  std::string bytes, err;
+  caffe_proto::Net net;
+  if (!slurp(argv[2], &bytes) || !caffe_proto::DecodeNet(bytes, &net)) { std::fprintf(stderr, "not a NetParameter file\n"); return 1; }
+  const int copied = caffe_proto::FlatFromNet(net, S, hidden, critic, flat.data(), &err);
+  if (copied < 0) { std::fprintf(stderr, "%s\n", err.c_str()); return 1; }
+  std::printf("layers copied: %d\n", copied);
+  return dump(argv[6], flat.data(), 4 * (size_t)n) ? 0 : 1;
+}
+
 int main(int argc, char **argv) {
+  if (argc > 1 && (std::string(argv[1]) == "--write-caffemodel" || std::string(argv[1]) == "--read-caffemodel")) return caffemodel_tool(argc, argv);
   if (argc > 1 && std::string(argv[1]) == "--gpu") {
     gpu_section();
     std::printf(failures ? "host_selftest --gpu: %d FAILURES\n" : "host_selftest --gpu: ok\n", failures);

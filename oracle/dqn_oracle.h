@@ -9,10 +9,15 @@
  * arithmetic lives in external Caffe @2ef584785c8ade90260eb117f189146364494183
  * (reference README.md:7-45), absent from this tree.  This oracle is therefore
  * pinned only against an independent float64 autograd derivation
- * (tests/test_oracle_autograd.py) and its own committed known-answer vectors
- * (tests/golden/), never against outputs of the reference itself.
+ * (tests/test_oracle_autograd.py), a second CPU model in Caffe's BLAS call
+ * order (tests/test_oracle_blas_order.py), a third-party implementation of the
+ * Caffe layers for the forward half (OpenCV's Caffe importer reading the
+ * nets as .caffemodel files, tests/test_caffemodel_opencv.py) and its own
+ * committed known-answer vectors (tests/golden/), never against outputs of
+ * the reference itself.
  *
- * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * Only tests/, __graft_entry__.smoke(), the parity block of bench.py --gpus N
+ * (scripts/dp_parity.py: checker only) and bench.py's cpu_baseline /
  * --impl reference legs may call anything in this file.
  */
 #ifndef DQN_ORACLE_H_
