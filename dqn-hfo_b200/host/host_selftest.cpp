@@ -118,7 +118,19 @@ static int caffemodel_tool(int argc, char **argv) {
   return dump(argv[6], flat.data(), 4 * (size_t)n) ? 0 : 1;
 }
 
+// --write-prototxt <out.prototxt> <actor|critic> <state_size> <h1,h2,..> <batch>: the net description dqn_main writes as
+// <prefix>_{actor,critic}.prototxt (dqn_main.cpp:232-246), for third-party parsers
+static int prototxt_tool(int argc, char **argv) {
+  if (argc != 7) { std::fprintf(stderr, "usage: %s --write-prototxt FILE actor|critic S H1,H2,.. BATCH\n", argv[0]); return 2; }
+  shim::set_flag("hidden", argv[5]);
+  const bool critic = std::string(argv[3]) == "critic";
+  const int S = std::atoi(argv[4]);
+  dqn::WriteNetPrototxt(critic ? dqn::CreateCriticNet(S) : dqn::CreateActorNet(S), argv[2], std::atoi(argv[6]));
+  return 0;
+}
+
 int main(int argc, char **argv) {
+  if (argc > 1 && std::string(argv[1]) == "--write-prototxt") return prototxt_tool(argc, argv);
   if (argc > 1 && (std::string(argv[1]) == "--write-caffemodel" || std::string(argv[1]) == "--read-caffemodel")) return caffemodel_tool(argc, argv);
   if (argc > 1 && std::string(argv[1]) == "--gpu") {
     gpu_section();

@@ -120,3 +120,25 @@ def test_opencv_leaky_relu_and_negative_inputs():
         expect = np.where(bias > 0, bias, np.float32(0.01) * bias)
         assert np.allclose(h1, np.broadcast_to(expect, (n, 64)), rtol=1e-6, atol=0)
         assert (h1[:, 10] == 0).all()
+
+
+@pytest.mark.parametrize("kind", ["actor", "critic"])
+def test_opencv_parses_the_prototxt_the_mirror_writes(tmp_path, kind):
+    """`<prefix>_{actor,critic}.prototxt` (dqn_main.cpp:232-246) as written by host/prototxt.cpp goes through OpenCV's
+    protobuf text-format parser with the real caffe.proto (MemoryData / InnerProduct / ReLU / Concat / Silence /
+    EuclideanLoss layers, `force_backward`, fillers): unknown fields or a malformed message would be a parse error."""
+    subprocess.run(["make", "-C", HOST, "host_selftest"], check=True, stdout=subprocess.DEVNULL)
+    f = tmp_path / f"{kind}.prototxt"
+    subprocess.run([os.path.join(HOST, "host_selftest"), "--write-prototxt", str(f), kind, "59", "1024,512,256,128", "32"], check=True)
+    text = f.read_text()
+    assert "force_backward: true" in text and 'type: "MemoryData"' in text
+    net = cv2.dnn.readNetFromCaffe(str(f))
+    names = list(net.getLayerNames())
+    want = ["state_input_layer"] + [n for i in range(1, 5) for n in (f"ip{i}_layer", f"ip{i}_relu_layer")]
+    want += ["action_input_layer", "action_params_input_layer", "target_input_layer", "concat", "q_values_layer", "loss"] if kind == "critic" \
+        else ["action_layer", "actionpara_layer"]
+    for n in want:
+        assert n in names, (n, names)
+    # tower order as in dqn.cpp:400-416
+    idx = [names.index(f"ip{i}_layer") for i in range(1, 5)]
+    assert idx == sorted(idx)
