@@ -192,8 +192,11 @@ def run_reference(args):
         "impl": "reference", "metric": "transition-updates/sec", "value": val, "unit": "transitions/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": dict(workload_config(args, 1), precision="fp32 on the host cores (CPU port of the reference's Caffe operation order)",
-                       parallelism=f"{cores} host threads"),
+        # the same config block as the native arm prints for these flags (the driver compares the two); how this arm runs
+        # the workload - fp32 on the host cores, no GPUs - is said in `implementation`
+        "config": workload_config(args, int(os.environ.get("WORLD_SIZE", "1"))),
+        "implementation": {"precision": "fp32 on the host cores (CPU port of the reference's Caffe operation order)",
+                           "parallelism": f"{cores} host threads, rank 0 only"},
         "cpu_baseline": {"value": val, "unit": "transitions/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "transitions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -202,16 +205,23 @@ def run_reference(args):
 
 
 def workload_config(args, world):
+    """The workload only (identical on both arms for the same flags; the driver compares the two blocks)."""
     return {
         "workload": f"cfg2: synthetic {args.state_size}-dim replay, {args.replay} stored transitions, "
                     f"batch {args.batch} UpdateActorCritic per GPU",
         "state_size": args.state_size, "batch_per_gpu": args.batch, "global_batch": args.batch * world,
-        "hidden": list(args.hidden), "replay_transitions": args.replay,
+        "hidden": list(args.hidden), "replay_transitions": args.replay, "ranks": world,
+        "l2": "replay ring (0.6 GB) exceeds L2; weights/activations are L2-resident by design of the workload",
+    }
+
+
+def implementation_note(args, world):
+    """How THIS arm runs the workload (not part of `config`)."""
+    return {
         "parallelism": (f"dp{world} (replay sharded; gradient exchange: " +
                         ("fused reduce-scatter/all-gather kernel over NVLink peer memory)" if getattr(args, "comm", "p2p") == "p2p"
                          else "ncclAllReduce)")) if world > 1 else "single GPU",
         "precision": "3xTF32 split-fp32 operands on tcgen05 (fp32-faithful: parity mode == benchmarked mode)",
-        "l2": "replay ring (0.6 GB) exceeds L2; weights/activations are L2-resident by design of the workload",
     }
 
 
@@ -407,7 +417,8 @@ def main():
         "metric": "transition-updates/sec", "value": value, "unit": "transitions/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (3xTF32 tensor-core products, fp32 accumulate)",
-        "data": "synthetic", "config": workload_config(args, world), "clocks": sampler.result(),
+        "data": "synthetic", "config": workload_config(args, world), "implementation": implementation_note(args, world),
+        "clocks": sampler.result(),
         "windows_ms_per_step": [w / args.steps for w in windows],
         "e2e": {"value": e2e_val, "unit": "transitions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "blocking_value": e2e_sync_val,
