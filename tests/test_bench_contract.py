@@ -29,6 +29,13 @@ def test_reference_arm_prints_the_contract_line():
     e2e = line["e2e"]
     assert e2e["value"] == line["value"] and e2e["h2d_bytes_per_step"] == 0 and e2e["d2h_bytes_per_step"] == 0
     assert "workload" in line["config"] and "model" not in line["config"]
+    # the config block names the workload only and is what the native arm prints for the same flags
+    import argparse
+    sys.path.insert(0, ROOT)
+    import bench
+    ns = argparse.Namespace(state_size=58, batch=256, hidden=[128, 64, 64, 32], replay=1_000_000)
+    assert line["config"] == bench.workload_config(ns, 1)
+    assert "precision" not in line["config"] and "host cores" in line["implementation"]["precision"]
 
 
 def test_reference_arm_other_ranks_exit_quietly():
