@@ -25,6 +25,10 @@ namespace dqn {
 
 using namespace hfo;
 
+struct DQN::ReplayGroup {
+  std::mutex mu;                    // guards `members`
+  std::vector<DQN *> members;
+};
 struct DQN::ShareGroup {
   std::mutex mu;
   std::vector<DQN *> members;
@@ -230,6 +234,11 @@ DQN::DQN(caffe::SolverParameter &actor_solver_param, caffe::SolverParameter &cri
 }
 
 DQN::~DQN() {
+  if (replay_share_) {
+    std::lock_guard<std::mutex> lock(replay_share_->mu);
+    auto &m = replay_share_->members;
+    m.erase(std::remove(m.begin(), m.end(), this), m.end());
+  }
   if (share_) {          // leave the sharing group: the others must not write through into a dead handle
     std::lock_guard<std::mutex> lock(share_->mu);
     std::lock_guard<std::recursive_mutex> self(mu_);
@@ -262,7 +271,12 @@ void DQN::refresh_iters() const {
 int DQN::critic_iter() const { refresh_iters(); return critic_iter_cache_; }
 int DQN::actor_iter() const { refresh_iters(); return actor_iter_cache_; }
 int DQN::memory_size() const { std::lock_guard<std::recursive_mutex> self(mu_); return dqnb_memory_size(h_); }
-void DQN::ClearReplayMemory() { std::lock_guard<std::recursive_mutex> self(mu_); DQNB_OK(dqnb_clear_memory(h_)); }
+void DQN::ClearReplayMemory() {
+  for (DQN *m : replay_targets()) {
+    std::lock_guard<std::recursive_mutex> lock(m->mu_);
+    DQNB_OK(dqnb_clear_memory(m->h_));
+  }
+}
 
 void DQN::Benchmark(int iterations) {
   std::lock_guard<std::recursive_mutex> self(mu_);
@@ -326,17 +340,31 @@ float DQN::EvaluateAction(const InputStates &input_states, const ActorOutput &ac
 }
 
 // ---- replay memory ------------------------------------------------------------------------------
-void DQN::AddTransition(const Transition &t) {
-  std::lock_guard<std::recursive_mutex> self(mu_);
+std::vector<DQN *> DQN::replay_targets() {
+  std::shared_ptr<ReplayGroup> grp;
+  { std::lock_guard<std::recursive_mutex> self(mu_); grp = replay_share_; }
+  if (!grp) return {this};
+  std::lock_guard<std::mutex> lock(grp->mu);
+  return grp->members;
+}
+// rows go into every ring of the replay group, one member at a time (no two object mutexes held together)
+void DQN::add_rows(int n, const float *s, const float *a, const float *r, const float *mc, const float *sn, const uint8_t *term) {
+  for (DQN *m : replay_targets()) {
+    std::lock_guard<std::recursive_mutex> lock(m->mu_);
+    DQNB_OK(dqnb_add_transitions(m->h_, n, s, a, r, mc, sn, term));
+  }
+}
 
+void DQN::AddTransition(const Transition &t) {   // dqn.cpp:768-773 (evicts when size == capacity)
   const auto &next = std::get<4>(t);
-  DQNB_OK(dqnb_add_transition(h_, std::get<0>(t)[kStateInputCount - 1]->data(), std::get<1>(t).data(), std::get<2>(t),
-                              std::get<3>(t), next ? (*next)->data() : nullptr, next ? 0 : 1));
+  for (DQN *m : replay_targets()) {
+    std::lock_guard<std::recursive_mutex> lock(m->mu_);
+    DQNB_OK(dqnb_add_transition(m->h_, std::get<0>(t)[kStateInputCount - 1]->data(), std::get<1>(t).data(), std::get<2>(t),
+                                std::get<3>(t), next ? (*next)->data() : nullptr, next ? 0 : 1));
+  }
 }
 
 void DQN::AddTransitions(const std::vector<Transition> &ts) {
-  std::lock_guard<std::recursive_mutex> self(mu_);
-
   const int n = (int)ts.size();
   if (n == 0) return;
   std::vector<float> s((size_t)n * state_size_), sn((size_t)n * state_size_, 0.f), a((size_t)n * 10), r(n), mc(n);
@@ -350,7 +378,7 @@ void DQN::AddTransitions(const std::vector<Transition> &ts) {
     term[i] = next ? 0 : 1;   // dqn.cpp:878: terminal <=> no next state
     if (next) std::copy((*next)->begin(), (*next)->end(), sn.begin() + (size_t)i * state_size_);
   }
-  DQNB_OK(dqnb_add_transitions(h_, n, s.data(), a.data(), r.data(), mc.data(), sn.data(), term.data()));
+  add_rows(n, s.data(), a.data(), r.data(), mc.data(), sn.data(), term.data());
 }
 
 void DQN::LabelTransitions(std::vector<Transition> &transitions) {  // dqn.cpp:783-797
@@ -624,8 +652,6 @@ void DQN::SnapshotReplayMemory(const std::string &filename) {
 }
 
 void DQN::LoadReplayMemory(const std::string &filename) {
-  std::lock_guard<std::recursive_mutex> self(mu_);
-
   CHECK(is_regular_file(filename)) << "Invalid file: " << filename;
   LOG(INFO) << "Loading replay memory from " << filename;
   ClearReplayMemory();
@@ -657,8 +683,8 @@ void DQN::LoadReplayMemory(const std::string &filename) {
   const int chunk = std::max(1, std::min(n, replay_memory_capacity_ / 2));
   for (int first = 0; first < n; first += chunk) {
     const int m = std::min(chunk, n - first);
-    DQNB_OK(dqnb_add_transitions(h_, m, s.data() + (size_t)first * state_size_, a.data() + (size_t)first * 10, r.data() + first,
-                                 mc.data() + first, sn.data() + (size_t)first * state_size_, t.data() + first));
+    add_rows(m, s.data() + (size_t)first * state_size_, a.data() + (size_t)first * 10, r.data() + first,
+             mc.data() + first, sn.data() + (size_t)first * state_size_, t.data() + first);
   }
   LOG(INFO) << "replay_mem_size = " << memory_size() << " with " << episodes << " episodes";
 }
@@ -699,25 +725,42 @@ void DQN::ShareParameters(DQN &other, int num_actor_layers_to_share, int num_cri
   other.share_ = share_;
   share_->members.push_back(&other);
 }
-// dqn.cpp:1081-1083: `other.replay_memory_ = replay_memory_` is a COPY of the deque (of shared_ptr states) at the time of
-// the call, not an alias: the two memories diverge afterwards.
+// dqn.cpp:1081-1083: `other.replay_memory_ = replay_memory_` - replay_memory_ is a shared_ptr (dqn.hpp:187), so from here
+// on the two DQNs use ONE deque (dqn_main.cpp:146-149, :359-363 wrap its users in a global mutex).  `other`'s ring takes
+// the owner's contents now and joins the owner's replay group: every later append / clear / load reaches every member.
 void DQN::ShareReplayMemory(DQN &other) {
   CHECK(&other != this);
   CHECK_EQ(state_size_, other.state_size_);
-  std::shared_ptr<ShareGroup> grp = share_;               // a group's updates reach into teammates too: same lock order
-  std::unique_lock<std::mutex> glock;
-  if (grp) glock = std::unique_lock<std::mutex>(grp->mu);
-  std::lock_guard<std::recursive_mutex> self(mu_);
-  std::lock_guard<std::recursive_mutex> mate(other.mu_);
-  other.ClearReplayMemory();
+  CHECK_EQ(replay_memory_capacity_, other.replay_memory_capacity_) << "a shared replay memory has one capacity";
+  std::shared_ptr<ReplayGroup> grp;
+  {
+    std::lock_guard<std::recursive_mutex> self(mu_);
+    if (!replay_share_) {
+      replay_share_ = std::make_shared<ReplayGroup>();
+      replay_share_->members.push_back(this);
+    }
+    grp = replay_share_;
+  }
+  std::lock_guard<std::mutex> glock(grp->mu);                 // no member list changes / group-wide appends meanwhile
   const int n = memory_size(), S = state_size_, chunk = 16384;
   std::vector<float> s((size_t)chunk * S), sn((size_t)chunk * S), a((size_t)chunk * (kActionSize + kActionParamSize)), r(chunk), mc(chunk);
   std::vector<uint8_t> term(chunk);
+  {
+    std::lock_guard<std::recursive_mutex> mate(other.mu_);
+    DQNB_OK(dqnb_clear_memory(other.h_));
+  }
   for (int first = 0; first < n; first += chunk) {
     const int m = std::min(chunk, n - first);
-    DQNB_OK(dqnb_get_transitions(h_, first, m, s.data(), a.data(), r.data(), mc.data(), sn.data(), term.data()));
+    {
+      std::lock_guard<std::recursive_mutex> self(mu_);
+      DQNB_OK(dqnb_get_transitions(h_, first, m, s.data(), a.data(), r.data(), mc.data(), sn.data(), term.data()));
+    }
+    std::lock_guard<std::recursive_mutex> mate(other.mu_);
     DQNB_OK(dqnb_add_transitions(other.h_, m, s.data(), a.data(), r.data(), mc.data(), sn.data(), term.data()));
   }
+  std::lock_guard<std::recursive_mutex> mate(other.mu_);
+  other.replay_share_ = grp;
+  grp->members.push_back(&other);
 }
 
 }  // namespace dqn

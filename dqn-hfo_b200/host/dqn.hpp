@@ -141,6 +141,14 @@ class DQN {
   // (ShareData aliases memory upstream; here the member that just updated writes its shared layers through to the others)
   struct ShareGroup;
   std::shared_ptr<ShareGroup> share_;
+  // ShareReplayMemory (dqn.cpp:1081-1083) makes two DQNs point at ONE deque (replay_memory_ is a shared_ptr, dqn.hpp:187).
+  // Every handle owns its ring in HBM, so the members of a replay group keep identical rings: what one member appends,
+  // clears or loads is applied to every member's ring (same capacity, same eviction rule -> same contents), and each
+  // samples its own copy.
+  struct ReplayGroup;
+  std::shared_ptr<ReplayGroup> replay_share_;
+  std::vector<DQN *> replay_targets();          // this object, or every member of its replay group
+  void add_rows(int n, const float *s, const float *a, const float *r, const float *mc, const float *sn, const uint8_t *term);
   // A handle is thread-compatible, not thread-safe (like a Caffe net).  Upstream every DQN is used by its own agent
   // thread only - except that thread 0 reaches into its teammates' objects to share layers / replay memory while they
   // are already playing (dqn_main.cpp:305-323) and, here, a member's update writes its shared layers into the others'

@@ -214,6 +214,16 @@ def test_dqn_main_two_agents_share_layers_and_replay(tmp_path):
         n = struct.unpack("<q", raw[12:20])[0]
         return raw[20:20 + 4 * n]
 
+    # ShareReplayMemory aliases ONE deque upstream (replay_memory_ is a shared_ptr): both agents' episodes land in both
+    # rings, so the two final memory snapshots hold (nearly) the same number of rows - they differ by at most the episodes
+    # appended between the two threads' final snapshots - and more than one agent alone collects in its ~60 env steps
+    import gzip
+    sizes = []
+    for agent in (0, 1):
+        f = sorted(glob.glob(prefix + f"_agent{agent}_*.replaymemory"))
+        assert f, (agent, sorted(os.listdir(tmp_path)))
+        sizes.append(struct.unpack("<i", gzip.open(f[-1], "rb").read(4))[0])
+    assert min(sizes) > 75 and abs(sizes[0] - sizes[1]) <= 2 * 41, sizes
     S = 59
     for kind, k_in in (("actor", S), ("critic", S + 10)):
         a, b = weights(0, kind), weights(1, kind)
